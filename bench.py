@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- fused unproject -> fuse -> project throughput (voxel-samples/s) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port on host cores)
+
+Workload "T" (BASELINE.md section 4 / SURVEY.md section 8(d)): 8-view InteriorNet-shaped scenes, 256-ch P4
+features 40x40 (640x640 padded input), 64^3 voxel grid, sum fusion, proj_grid P=40, S=20.
+One *step* = one pass of the pipeline over a batch of ``--scenes`` synthetic scenes per GPU;
+scenes are independent, so ranks shard scenes with no data-path collective (weak scaling).
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "voxel_samples_per_s"
+UNIT = "voxel-samples/s"
+T = dict(V=8, C=256, nvox=64, fh=40, fw=40, P=40, S=20, image=640)
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def make_config(B):
+    from mulit_view_object_detection_b200.config import FusionConfig
+    return FusionConfig(nvox=T["nvox"], nvox_z=T["nvox"], samples=T["S"], NUM_VIEWS=T["V"], GRID_REAS="add",
+                        IMAGES_PER_GPU=B, IMAGE_SHAPE=np.array([T["image"], T["image"], 3]),
+                        TOP_DOWN_PYRAMID_SIZE=T["C"])
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "T: %d-view scene, 256-ch P4 40x40 features, 64^3 grid, unproject->sum-fuse->project(P=40,S=20), fp32"
+                        % T["V"],
+            "scenes_per_gpu": args.scenes, "views": T["V"], "grid": [T["nvox"]] * 3, "channels": T["C"],
+            "feature_hw": [T["fh"], T["fw"]], "proj": T["P"], "samples": T["S"],
+            "sharding": "scenes sharded across ranks, no data-path collective" if n_gpus > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2: per-step working set = %d scenes x 347 MB (features %.0f MB, grids %.0f MB)"
+                         % (args.scenes, args.scenes * 13.1, args.scenes * 268.4)}
+
+
+def algorithmic_bytes(B):
+    """B_alg = 4*C*(V*fh*fw + N + 2*S*P*P) per scene; K1 = read every feature vector once
+    + write the fused grid once; K3 = read one grid vector + write one output vector per ray sample."""
+    N = T["nvox"] ** 3
+    k1 = 4 * T["C"] * (T["V"] * T["fh"] * T["fw"] + N) * B
+    k3 = 4 * T["C"] * (2 * T["S"] * T["P"] * T["P"]) * B
+    return k1, k3
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.reasons, self.stop_flag = period, [], set(), False
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def k1_traffic_bytes(B):
+    """dram bytes per K1 launch from the committed ncu capture (profiles/k1_traffic.json), scaled to B scenes."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        return float(d["dram_bytes_per_scene"]) * B
+    except Exception:
+        return None
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(scenes, slab, steps, warmup, threads=None):
+    """The oracle's torch-CPU port (the stand-in for the reference's TF CPU path) on a bounded
+    sample: ``scenes`` T-scenes restricted to an x-slab of ``slab`` of the 64 x-planes."""
+    import torch
+    from oracle import torch_cpu
+    from mulit_view_object_detection_b200 import synthetic as syn
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = make_config(scenes)
+    feats, Rcam, Kmat = syn.make_scene(cfg, scenes, T["V"], T["fh"], T["fw"], T["C"], seed=1234)
+    feats_t = torch.from_numpy(feats)
+    X = T["nvox"]
+    full = torch.zeros((scenes, X, X, X, T["C"]), dtype=torch.float32)
+
+    def step():
+        part = torch_cpu.unproject_fuse(feats_t, Rcam, Kmat, cfg, "sum", x_slab=(0, slab))
+        full[:, :slab] = part
+        return torch_cpu.project(full, Rcam, Kmat, cfg, T["P"])
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    samples = scenes * T["V"] * slab * X * X * steps
+    return samples / dt, dt / steps, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    slab = 8
+    value, s_per_step, threads = cpu_reference_run(1, slab, args.steps, min(args.warmup, 1))
+    sample = "1 scene of workload T restricted to an x-slab of %d/64 planes (%d voxel-samples per step) + full proj_grid" \
+             % (slab, T["V"] * slab * 64 * 64)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "TensorFlow/Keras are not installable here (no wheel, no network) and TF-CPU gather_nd raises on this "
+                    "path's out-of-range taps; this arm times oracle/torch_cpu.py, the op-for-op torch-CPU port of the "
+                    "reference graph, on all host threads"}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import mulit_view_object_detection_b200 as m
+    from mulit_view_object_detection_b200 import synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.scenes
+    cfg = make_config(B)
+    stream = torch.cuda.current_stream()
+
+    # synthetic scenes: one seeded scene block per rank, resident in HBM before the timed region
+    feats, Rcam, Kmat = syn.make_scene(cfg, B, T["V"], T["fh"], T["fw"], T["C"], seed=1000 + rank)
+    d_feats, d_R, d_K = (torch.from_numpy(a).to(dev) for a in (feats, Rcam, Kmat))
+    X = T["nvox"]
+    grid = torch.empty((B, X, X, X, T["C"]), dtype=torch.float32, device=dev)
+    rays = torch.empty((B, T["S"], T["P"], T["P"], T["C"]), dtype=torch.float32, device=dev)
+
+    def step():
+        m.unproject_fuse(d_feats, d_R, d_K, cfg, mode="sum", out=grid)
+        m.proj_grid([grid, d_R, d_K], cfg, T["P"], out=rays)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: device-resident inputs; per-kernel CUDA events on the launching stream
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    n0 = m.launch_count()
+    barrier()
+    for k in range(K):
+        ev[k][0].record(stream)
+        m.unproject_fuse(d_feats, d_R, d_K, cfg, mode="sum", out=grid)
+        ev[k][1].record(stream)
+        m.proj_grid([grid, d_R, d_K], cfg, T["P"], out=rays)
+        ev[k][2].record(stream)
+    barrier()
+    launches = m.launch_count() - n0
+    clocks = sampler.result()
+    total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
+    k1_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    k3_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    voxel_samples_step = world * B * T["V"] * X ** 3
+    value = voxel_samples_step * K / (total_ms * 1e-3)
+
+    # ---- end to end through the C-ABI host entry: pinned host buffers in, pinned ray slices out
+    pipe = m.HostPipeline(cfg, B, T["V"], T["fh"], T["fw"], T["C"], T["P"], mode="sum")
+    h_in = [torch.from_numpy(a).pin_memory() for a in (feats, Rcam, Kmat)]
+    h_out = pipe.empty_output()
+    for _ in range(3):
+        pipe(h_in[0], h_in[1], h_in[2], h_out)
+    barrier()
+    Ke = max(3, min(K, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(Ke):
+        pipe(h_in[0], h_in[1], h_in[2], h_out)
+    e1.record(stream)
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = voxel_samples_step * Ke / (float(te.item()) * 1e-3)
+    checksum = float(h_out.double().sum())          # the device->host result is really read
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        k1_bytes, k3_bytes = algorithmic_bytes(B)
+        achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                    "steps": Ke, "api": "mvf_unproject_fuse_project_host (pinned host buffers, H2D + K1 + K3 + D2H + sync)",
+                    "checksum": checksum},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "unproject_fuse_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": k1_traffic_bytes(B), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
+                         "share_of_step": k1_ms / (k1_ms + k3_ms)},
+            "pipeline": {"algorithmic_bytes_per_step": k1_bytes + k3_bytes, "achieved_gbs": (k1_bytes + k3_bytes) / (total_ms / K * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": (k1_bytes + k3_bytes) / (total_ms / K * 1e-3) / 1e9 / peak,
+                         "k1_ms": k1_ms, "k3_ms": k3_ms,
+                         "k3_achieved_gbs": k3_bytes / (k3_ms * 1e-3) / 1e9},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, s_per, threads = cpu_reference_run(1, 8, 1, 0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "1 scene of workload T, x-slab 8/64 of the grid (262144 voxel-samples) + full "
+                                              "proj_grid, oracle/torch_cpu.py on all host threads, %.1f s" % s_per}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

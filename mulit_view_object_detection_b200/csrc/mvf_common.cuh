@@ -1,0 +1,90 @@
+// Shared device/host helpers for libmvfusion (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <atomic>
+#include "mvfusion.h"
+
+namespace mvf {
+
+extern std::atomic<unsigned long long> g_launches;
+
+inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+inline int check_launch() {
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MVF_OK : MVF_ECUDA;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- pinned fp32 arithmetic: every op individually rounded, no FMA contraction --------------
+// (dot products left-to-right in ascending k).
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+
+__device__ __forceinline__ float dot3_rn(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return add_rn(add_rn(mul_rn(a0, b0), mul_rn(a1, b1)), mul_rn(a2, b2));
+}
+__device__ __forceinline__ float dot4_rn(float a0, float a1, float a2, float a3,
+                                         float b0, float b1, float b2, float b3) {
+    return add_rn(add_rn(add_rn(mul_rn(a0, b0), mul_rn(a1, b1)), mul_rn(a2, b2)), mul_rn(a3, b3));
+}
+
+// [R^T | -(R^T t)] of a camera->world pose P (3x4 row-major) -> out (3x4 row-major)
+// mrcnn/model_multi.py:137-143 / :279-281
+__device__ __forceinline__ void inverse_pose(const float* P, float* out) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float r0 = P[0 * 4 + i], r1 = P[1 * 4 + i], r2 = P[2 * 4 + i];   // row i of R^T
+        out[i * 4 + 0] = r0; out[i * 4 + 1] = r1; out[i * 4 + 2] = r2;
+        out[i * 4 + 3] = -dot3_rn(r0, r1, r2, P[3], P[7], P[11]);
+    }
+}
+
+// 3x4 . (x,y,z,1) row i, ascending k; the homogeneous 1 multiplies exactly.
+__device__ __forceinline__ float affine_row(const float* M, int i, float x, float y, float z) {
+    return add_rn(add_rn(add_rn(mul_rn(M[i * 4 + 0], x), mul_rn(M[i * 4 + 1], y)),
+                         mul_rn(M[i * 4 + 2], z)), M[i * 4 + 3]);
+}
+
+__device__ __forceinline__ bool usable_coord(float v) {
+    return (fabsf(v) < 1073741824.0f);      // finite and |v| < 2^30 (NaN compares false)
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stcs4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float4 fma4(float w, float4 f, float4 a) {
+    a.x = fmaf(w, f.x, a.x); a.y = fmaf(w, f.y, a.y); a.z = fmaf(w, f.z, a.z); a.w = fmaf(w, f.w, a.w);
+    return a;
+}
+__device__ __forceinline__ float4 mul4(float w, float4 f) { return make_float4(w * f.x, w * f.y, w * f.z, w * f.w); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 max4(float4 a, float4 b) { return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w)); }
+__device__ __forceinline__ float4 relu4(float4 a) { return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)); }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// ---- host: TF1 RangeOp<float> / LinSpaceOp<float> fill order ---------------------------------
+// (third-party kernels restated; call sites mrcnn/model_multi.py:157-160, :267)
+inline int tf1_range(double start_d, double limit_d, double delta_d, float* out, int cap) {
+    const float start = (float)start_d, limit = (float)limit_d, delta = (float)delta_d;
+    volatile float q = (limit - start) / delta;           // volatile: keep it a rounded float
+    const int size = (int)ceilf(fabsf(q));
+    if (size > cap || size < 0) return -1;
+    volatile float val = start;
+    for (int i = 0; i < size; ++i) { out[i] = val; val = val + delta; }
+    return size;
+}
+inline void tf1_linspace(double start_d, double stop_d, int num, float* out) {
+    const float start = (float)start_d, stop = (float)stop_d;
+    if (num == 1) { out[0] = start; return; }
+    volatile float step = (stop - start) / (float)(num - 1);
+    for (int i = 0; i < num; ++i) { volatile float m = step * (float)i; out[i] = start + m; }
+}
+
+}  // namespace mvf

@@ -1,0 +1,288 @@
+// K1  unproject_fuse: unproj_feat (+ fused view reduction / BN / ReLU) for sm_100a.
+//
+// Replaces mrcnn/model_multi.py:130-228 (unproj_feat) and :401-404 (grid_reas 'add'), plus the
+// world-frame notebook variant Notebook/projection.py:47-151.  The per-view grids
+// [B,V,X,Y,Z,C] are never materialised unless mode == MVF_FUSE_NONE.
+//
+// Mapping: one CTA = one 4x4x16 brick of voxels of one scene; a warp owns 32 voxels of the
+// brick.  Lanes first work as 32 independent (voxel, view) coordinate units -- voxel->pixel
+// projection, floor, the four weights and the tap-validity bits are computed ONCE per pair in
+// registers with individually rounded fp32 ops (bit-exact against the oracle) -- and then the
+// warp walks the 32 pairs: every pair's parameters are broadcast with shuffles and the 32 lanes
+// become 32 float4 channel slots, so every tap is one coalesced 128-bit read-only load per lane
+// (512 B per warp instruction) and every voxel one coalesced streaming 128-bit store.
+// The view reduction lives in the accumulator registers.
+#include "mvf_common.cuh"
+
+namespace mvf {
+
+constexpr int BRICK_X = 4, BRICK_Y = 4, BRICK_Z = 16;
+constexpr int K1_THREADS = 256;
+constexpr int K1_WARPS = K1_THREADS / 32;
+static_assert(BRICK_X * BRICK_Y * BRICK_Z == K1_WARPS * 32, "one voxel per (warp, lane)");
+
+struct UnprojParams {
+    const float* feats; const float* Rcam; const float* Rmain; const float* Kmat;
+    const float* bn_scale; const float* bn_shift;
+    float* out; int32_t* out_idx; uint8_t* out_valid; float* out_grid_pos;
+    int B, V, fh, fw, C, X, Y, Z, x_begin, Xs;
+    int mode, flags;
+    float sx, sy, inv_v, grid_dist;
+    float gx[MVF_MAX_DIM], gy[MVF_MAX_DIM], gz[MVF_MAX_DIM];
+};
+
+template <int CPL, int MODE>
+__global__ void __launch_bounds__(K1_THREADS)
+unproject_fuse_kernel(const __grid_constant__ UnprojParams p) {
+    __shared__ float sKR[MVF_MAX_VIEWS][12];
+    __shared__ float sOff[3];
+
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const bool world = (p.flags & MVF_FLAG_WORLD_GRID) != 0;
+
+    // ---- prologue: KR_v = (K . [R_v^T | -R_v^T t_v]) . [[R_0|t_0],[0 0 0 1]]   (:137-147, :175-180)
+    if (tid < p.V) {
+        const float* P = p.Rcam + ((size_t)b * p.V + tid) * 12;
+        const float* K = p.Kmat + (size_t)b * 9;
+        const float* P0 = p.Rmain ? p.Rmain + (size_t)b * 12 : p.Rcam + (size_t)b * p.V * 12;
+        float Rinv[12], M[12];
+        inverse_pose(P, Rinv);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                M[i * 4 + j] = dot3_rn(K[i * 3 + 0], K[i * 3 + 1], K[i * 3 + 2],
+                                       Rinv[0 * 4 + j], Rinv[1 * 4 + j], Rinv[2 * 4 + j]);
+        if (world) {
+#pragma unroll
+            for (int e = 0; e < 12; ++e) sKR[tid][e] = M[e];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float t3 = (j == 3) ? 1.0f : 0.0f;            // last row of T0
+                    sKR[tid][i * 4 + j] = dot4_rn(M[i * 4 + 0], M[i * 4 + 1], M[i * 4 + 2], M[i * 4 + 3],
+                                                  P0[0 * 4 + j], P0[1 * 4 + j], P0[2 * 4 + j], t3);
+                }
+        }
+    }
+    if (tid == 32 && world) {
+        // grid_position = [R0|t0] . (0,0,grid_dist,1)   (Notebook/projection.py:86-91)
+        const float* P0 = p.Rmain ? p.Rmain + (size_t)b * 12 : p.Rcam + (size_t)b * p.V * 12;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float v = dot4_rn(P0[i * 4 + 0], P0[i * 4 + 1], P0[i * 4 + 2], P0[i * 4 + 3],
+                                    0.0f, 0.0f, p.grid_dist, 1.0f);
+            sOff[i] = v;
+            if (p.out_grid_pos && blockIdx.x == 0) p.out_grid_pos[b * 3 + i] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- brick / voxel assignment
+    const int tiles_z = (p.Z + BRICK_Z - 1) / BRICK_Z;
+    const int tiles_y = (p.Y + BRICK_Y - 1) / BRICK_Y;
+    int t = blockIdx.x;
+    const int tz = t % tiles_z; t /= tiles_z;
+    const int ty = t % tiles_y; t /= tiles_y;
+    const int tx = t;
+    const int warp = tid >> 5, lane = tid & 31;
+    const unsigned FULL = 0xffffffffu;
+
+    const int C = p.C, V = p.V;
+    const int C4 = C >> 2;
+    const size_t view_stride = (size_t)p.fh * p.fw * C;
+    const float* feats_b = p.feats + (size_t)b * V * view_stride;
+    const int row_stride = p.fw * C;
+
+    float4 acc[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acc[k] = zero4();
+
+    const int npairs = 32 * V;
+    for (int q0 = 0; q0 < npairs; q0 += 32) {
+        // ---- phase 1: lane = one (voxel, view) pair
+        const int q = q0 + lane;
+        const int lv = q / V;                    // voxel slot 0..31 of this warp
+        const int v = q - lv * V;
+        const int l = warp * 32 + lv;            // voxel index inside the brick (z fastest)
+        const int iz = tz * BRICK_Z + (l % BRICK_Z);
+        const int iy = ty * BRICK_Y + ((l / BRICK_Z) % BRICK_Y);
+        const int ixs = tx * BRICK_X + (l / (BRICK_Z * BRICK_Y));      // index inside the slab
+        const bool in_grid = (iz < p.Z) && (iy < p.Y) && (ixs < p.Xs);
+        int my_bits = 0, my_off = 0;
+        float wa = 0.f, wb = 0.f, wc = 0.f, wd = 0.f;
+        if (in_grid) {
+            float x = p.gx[p.x_begin + ixs], y = p.gy[iy], z = p.gz[iz];
+            if (world) { x = add_rn(x, sOff[0]); y = add_rn(y, sOff[1]); z = add_rn(z, sOff[2]); }
+            const float* KR = sKR[v];
+            const float px = affine_row(KR, 0, x, y, z);
+            const float py = affine_row(KR, 1, x, y, z);
+            const float pz = affine_row(KR, 2, x, y, z);
+            const float u = mul_rn(div_rn(px, pz), p.sx);               // :187
+            const float w = mul_rn(div_rn(py, pz), p.sy);               // :188
+            int x0 = INT32_MIN, y0 = INT32_MIN;
+            if (usable_coord(u) && usable_coord(w)) {
+                const float x0f = floorf(u), y0f = floorf(w);            // :192-195
+                x0 = (int)x0f; y0 = (int)y0f;
+                const float x1f = (float)(x0 + 1), y1f = (float)(y0 + 1);
+                const float ax = sub_rn(x1f, u), bx = sub_rn(u, x0f);
+                const float ay = sub_rn(y1f, w), by = sub_rn(w, y0f);
+                wa = mul_rn(ax, ay); wb = mul_rn(ax, by); wc = mul_rn(bx, ay); wd = mul_rn(bx, by);   // :214-217
+                const bool inx0 = (x0 >= 0) && (x0 < p.fw), inx1 = (x0 + 1 >= 0) && (x0 + 1 < p.fw);
+                const bool iny0 = (y0 >= 0) && (y0 < p.fh), iny1 = (y0 + 1 >= 0) && (y0 + 1 < p.fh);
+                my_bits = (int)(iny0 && inx0) | ((int)(iny1 && inx0) << 1) | ((int)(iny0 && inx1) << 2) |
+                          ((int)(iny1 && inx1) << 3);
+                if (my_bits) my_off = (y0 * p.fw + x0) * C;              // may be negative: only valid taps are read
+            }
+            const size_t vox = (((size_t)b * V + v) * p.Xs + ixs) * p.Y * p.Z + (size_t)iy * p.Z + iz;
+            if (p.out_idx) { p.out_idx[vox * 2 + 0] = y0; p.out_idx[vox * 2 + 1] = x0; }
+            if (p.out_valid) p.out_valid[vox] = (uint8_t)my_bits;
+            my_bits |= 16;                                               // bit4: voxel is inside the grid
+        }
+
+        // ---- phase 2: lanes = float4 channel slots; walk the 32 pairs of this chunk
+        const int jmax = min(32, npairs - q0);
+        for (int j = 0; j < jmax; ++j) {
+            const int bits = __shfl_sync(FULL, my_bits, j);
+            const int qq = q0 + j;
+            const int jlv = qq / V;
+            const int jv = qq - jlv * V;
+            if (!(bits & 16)) continue;                                  // warp-uniform
+            float4 val[CPL];
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) val[k] = zero4();
+            if (bits & 15) {
+                const int off = __shfl_sync(FULL, my_off, j);
+                const float fa = __shfl_sync(FULL, wa, j), fb = __shfl_sync(FULL, wb, j);
+                const float fc = __shfl_sync(FULL, wc, j), fd = __shfl_sync(FULL, wd, j);
+                const float* base = feats_b + (size_t)jv * view_stride + off;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int c4 = lane + 32 * k;
+                    if (c4 < C4) {
+                        const float* pc = base + 4 * c4;
+                        if (bits & 1) val[k] = fma4(fa, ldg4(pc), val[k]);
+                        if (bits & 2) val[k] = fma4(fb, ldg4(pc + row_stride), val[k]);
+                        if (bits & 4) val[k] = fma4(fc, ldg4(pc + C), val[k]);
+                        if (bits & 8) val[k] = fma4(fd, ldg4(pc + row_stride + C), val[k]);
+                    }
+                }
+            }
+            if (p.flags & MVF_FLAG_RELU_IN) {
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) val[k] = relu4(val[k]);
+            }
+            // voxel coordinates of pair j (warp-uniform)
+            const int jl = warp * 32 + jlv;
+            const int jz = tz * BRICK_Z + (jl % BRICK_Z);
+            const int jy = ty * BRICK_Y + ((jl / BRICK_Z) % BRICK_Y);
+            const int jx = tx * BRICK_X + (jl / (BRICK_Z * BRICK_Y));
+            if (MODE == MVF_FUSE_NONE) {
+                float* o = p.out + ((((size_t)b * V + jv) * p.Xs + jx) * p.Y * p.Z + (size_t)jy * p.Z + jz) * C;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int c4 = lane + 32 * k;
+                    if (c4 < C4) stcs4(o + 4 * c4, val[k]);
+                }
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+                if (MODE == MVF_FUSE_MAX) acc[k] = (jv == 0) ? val[k] : max4(acc[k], val[k]);
+                else acc[k] = (jv == 0) ? val[k] : add4(acc[k], val[k]);
+            }
+            if (jv == V - 1) {
+                float* o = p.out + ((((size_t)b * p.Xs + jx) * p.Y + jy) * p.Z + jz) * C;
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) {
+                    const int c4 = lane + 32 * k;
+                    if (c4 < C4) {
+                        float4 r = acc[k];
+                        if (MODE == MVF_FUSE_MEAN) r = mul4(p.inv_v, r);
+                        if (p.bn_scale) {
+                            const float4 s = ldg4(p.bn_scale + 4 * c4), h = ldg4(p.bn_shift + 4 * c4);
+                            r = make_float4(fmaf(r.x, s.x, h.x), fmaf(r.y, s.y, h.y), fmaf(r.z, s.z, h.z), fmaf(r.w, s.w, h.w));
+                        }
+                        if (p.flags & MVF_FLAG_RELU_OUT) r = relu4(r);
+                        stcs4(o + 4 * c4, r);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int CPL>
+static int launch_k1(const UnprojParams& p, dim3 grid, cudaStream_t s) {
+    switch (p.mode) {
+        case MVF_FUSE_NONE: unproject_fuse_kernel<CPL, MVF_FUSE_NONE><<<grid, K1_THREADS, 0, s>>>(p); break;
+        case MVF_FUSE_SUM:  unproject_fuse_kernel<CPL, MVF_FUSE_SUM><<<grid, K1_THREADS, 0, s>>>(p); break;
+        case MVF_FUSE_MEAN: unproject_fuse_kernel<CPL, MVF_FUSE_MEAN><<<grid, K1_THREADS, 0, s>>>(p); break;
+        case MVF_FUSE_MAX:  unproject_fuse_kernel<CPL, MVF_FUSE_MAX><<<grid, K1_THREADS, 0, s>>>(p); break;
+        default: return MVF_EINVAL;
+    }
+    count_launch();
+    return check_launch();
+}
+
+// Fill the voxel-centre arrays the way the reference's tf.range calls do.
+int fill_centres(const MvfGrid* g, int flags, float* gx, float* gy, float* gz) {
+    if (g->nvox <= 0 || g->nvox_z <= 0 || g->nvox > MVF_MAX_DIM || g->nvox_z > MVF_MAX_DIM) return MVF_EUNSUPPORTED;
+    const int nx = tf1_range(g->vmin + g->vsize / 2.0, g->vmax, g->vsize, gx, MVF_MAX_DIM);   // :157
+    if (nx != g->nvox) return MVF_EINVAL;
+    for (int i = 0; i < nx; ++i) gy[i] = gx[i];
+    int nz;
+    if (flags & MVF_FLAG_WORLD_GRID)      // Notebook/projection.py:80
+        nz = tf1_range(-(g->nvox_z - 1) * 0.5 * g->vsize, (g->nvox_z - 1) * 0.5 * g->vsize + g->vsize / 2, g->vsize, gz, MVF_MAX_DIM);
+    else                                  // model_multi.py:159
+        nz = tf1_range(g->vmin_z + g->vsize_z / 2.0, g->vmax_z, g->vsize_z, gz, MVF_MAX_DIM);
+    if (nz != g->nvox_z) return MVF_EINVAL;
+    return MVF_OK;
+}
+
+}  // namespace mvf
+
+using namespace mvf;
+
+extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat,
+                                  const MvfGrid* g, int B, int V, int fh, int fw, int C, int img_h, int img_w,
+                                  int mode, int flags, double grid_dist, int x_begin, int x_count,
+                                  const float* bn_scale, const float* bn_shift,
+                                  float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
+                                  void* stream) {
+    if (!feats || !Rcam || !Kmat || !g || !out) return MVF_ENULL;
+    if (B <= 0 || V <= 0 || fh <= 0 || fw <= 0 || C <= 0 || img_h <= 0 || img_w <= 0) return MVF_EINVAL;
+    if (mode < MVF_FUSE_NONE || mode > MVF_FUSE_MAX) return MVF_EINVAL;
+    if ((bn_scale == nullptr) != (bn_shift == nullptr)) return MVF_ENULL;
+    if (C % 4 != 0 || !aligned16(feats) || !aligned16(out) || (bn_scale && (!aligned16(bn_scale) || !aligned16(bn_shift))))
+        return MVF_EALIGN;
+    if (V > MVF_MAX_VIEWS || C > 1024 || B > 65535) return MVF_EUNSUPPORTED;
+    if ((size_t)fh * fw * C >= (size_t)1 << 31) return MVF_EUNSUPPORTED;
+    UnprojParams p;
+    int rc = fill_centres(g, flags, p.gx, p.gy, p.gz);
+    if (rc != MVF_OK) return rc;
+    if (x_count == 0) { x_begin = 0; x_count = g->nvox; }
+    if (x_begin < 0 || x_count < 0 || x_begin + x_count > g->nvox) return MVF_EINVAL;
+    p.feats = feats; p.Rcam = Rcam; p.Rmain = Rmain; p.Kmat = Kmat;
+    p.bn_scale = (mode == MVF_FUSE_NONE) ? nullptr : bn_scale;
+    p.bn_shift = (mode == MVF_FUSE_NONE) ? nullptr : bn_shift;
+    p.out = out; p.out_idx = out_idx; p.out_valid = out_valid; p.out_grid_pos = out_grid_pos;
+    p.B = B; p.V = V; p.fh = fh; p.fw = fw; p.C = C;
+    p.X = g->nvox; p.Y = g->nvox; p.Z = g->nvox_z; p.x_begin = x_begin; p.Xs = x_count;
+    p.mode = mode; p.flags = (mode == MVF_FUSE_NONE) ? (flags & ~MVF_FLAG_RELU_OUT) : flags;
+    p.sy = (float)((double)fh / (double)img_h);          // :153  float(fh) / IMAGE_SHAPE[0]
+    p.sx = (float)((double)fw / (double)img_w);          // :154
+    p.inv_v = 1.0f / (float)V;
+    p.grid_dist = (float)grid_dist;
+    const int tiles = ((p.Xs + BRICK_X - 1) / BRICK_X) * ((p.Y + BRICK_Y - 1) / BRICK_Y) * ((p.Z + BRICK_Z - 1) / BRICK_Z);
+    dim3 grid(tiles, B);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int C4 = C / 4;
+    if (C4 <= 32) return launch_k1<1>(p, grid, s);
+    if (C4 <= 64) return launch_k1<2>(p, grid, s);
+    if (C4 <= 128) return launch_k1<4>(p, grid, s);
+    return launch_k1<8>(p, grid, s);
+}

@@ -1,0 +1,537 @@
+"""Host-side mirror of the reference's fusion-path layers over libmvfusion.so.
+
+Same names, argument order, ``config`` attribute names and output layouts as the Keras/TF1
+layers in mrcnn/model_multi.py and mrcnn/recurrent.py, operating on contiguous fp32
+channel-last **torch CUDA tensors** in place of TF tensors:
+
+    unproj_feat([feats, Rcam, Kmat], config)                      model_multi.py:130
+    grid_reas(x, scope, config)                                   model_multi.py:394
+    convlstm(grid, name, kernel, filters)                         model_multi.py:109
+    proj_grid([grid, Rcam, Kmat], config, proj_size)              model_multi.py:231
+    depth_sampling(x, config, name)                               model_multi.py:466
+    PyramidROIAlign(pool_shape)([boxes, image_meta] + maps)       model_multi.py:779
+    refine_detections_graph(rois, probs, deltas, window, config)  model_multi.py:1119
+    DetectionLayer(config)([rois, cls, bbox, image_meta])         model_multi.py:1217
+    ProposalLayer(count, nms_thr, config)([probs, bbox, anchors]) model_multi.py:690
+
+plus the fused entries ``unproject_fuse`` / ``unproject_fuse_project`` that never materialise
+the per-view grids.  torch is plumbing only (device memory, streams); every op is a kernel of
+libmvfusion.so launched on ``torch.cuda.current_stream()``.  There is no CPU path: a non-CUDA
+tensor raises ``ValueError`` (the reference raises on CPU too -- TF-CPU ``gather_nd`` rejects
+the out-of-range taps this path produces).
+
+Learnable state (frozen inference weights) is looked up by layer scope/name in ``weights``,
+mirroring the reference's ``reused_lay`` registry (model_multi.py:112-117); missing entries
+use the Keras initial values (BatchNorm gamma=1, beta=0, mean=0, var=1).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, grid_from_config
+
+BN_EPS = 1e-3                      # Keras BatchNormalization default (model_multi.py:501-502)
+
+# scope/name -> dict of tensors; the analogue of the reference's `reused_lay`
+weights = {}
+reused_lay = weights
+
+
+def set_weights(scope, **tensors):
+    weights[scope] = tensors
+
+
+# ------------------------------------------------------------------------------------------------
+def _cuda(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError("%s must be a torch tensor (got %r)" % (name, type(t)))
+    if not t.is_cuda:
+        raise ValueError("%s must live on a CUDA device: this path has no CPU implementation" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s (got %s)" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _bn_affine(bn, C_, device):
+    """(scale, shift) of a frozen BatchNorm as tf.nn.batch_normalization evaluates it:
+    inv = rsqrt(var + eps) * gamma ; shift = beta - mean * inv."""
+    if bn is None:
+        return None, None
+    gamma, beta, mean, var = (torch.as_tensor(a, dtype=torch.float32, device=device).reshape(-1) for a in bn)
+    inv = torch.rsqrt(var + BN_EPS) * gamma
+    shift = beta - mean * inv
+    if inv.numel() == 1 and C_ > 1:
+        inv, shift = inv.expand(C_), shift.expand(C_)
+    return inv.contiguous(), shift.contiguous()
+
+
+def _default_bn(C_):
+    return (np.ones(C_, np.float32), np.zeros(C_, np.float32), np.zeros(C_, np.float32), np.ones(C_, np.float32))
+
+
+def _image_hw(config):
+    return int(config.IMAGE_SHAPE[0]), int(config.IMAGE_SHAPE[1])
+
+
+_FUSE = {"none": _lib.FUSE_NONE, "sum": _lib.FUSE_SUM, "add": _lib.FUSE_SUM, "mean": _lib.FUSE_MEAN,
+         "max": _lib.FUSE_MAX}
+
+
+# ------------------------------------------------------------------------------------------------
+def unproject_fuse(feats, Rcam, Kmat, config, mode="sum", bn=None, relu_in=False, relu_out=False,
+                   Rmain=None, x_slab=None, world_grid=False, return_aux=False, out=None):
+    """K1: unproject every view and reduce over views in registers.
+
+    mode 'none' -> [B,V,Xs,Y,Z,C] (= unproj_feat), else [B,Xs,Y,Z,C].
+    ``Rmain`` [B,3,4]: main-view pose when ``Rcam`` is a shard of the views.
+    ``x_slab`` (x_begin, x_count): compute one x-slab of the grid only.
+    ``return_aux``: also return idx int32 [B,V,Xs,Y,Z,2] and valid uint8 [B,V,Xs,Y,Z]."""
+    feats = _cuda(feats, "feats")
+    Rcam = _cuda(Rcam, "Rcam")
+    Kmat = _cuda(Kmat, "Kmat")
+    if feats.dim() != 5 or Rcam.dim() != 4 or Kmat.dim() != 3:
+        raise ValueError("expected feats [B,V,fh,fw,C], Rcam [B,V,3,4], Kmat [B,3,3]")
+    B, V, fh, fw, Cc = feats.shape
+    if tuple(Rcam.shape) != (B, V, 3, 4) or tuple(Kmat.shape) != (B, 3, 3):
+        raise ValueError("Rcam %s / Kmat %s do not match feats %s" % (tuple(Rcam.shape), tuple(Kmat.shape), tuple(feats.shape)))
+    if Rmain is not None:
+        Rmain = _cuda(Rmain, "Rmain")
+        if tuple(Rmain.shape) != (B, 3, 4):
+            raise ValueError("Rmain must be [B,3,4]")
+    g = grid_from_config(config)
+    xb, xc = (0, g.nvox) if x_slab is None else (int(x_slab[0]), int(x_slab[1]))
+    Y, Z = g.nvox, g.nvox_z
+    m = _FUSE[mode]
+    shape = (B, V, xc, Y, Z, Cc) if m == _lib.FUSE_NONE else (B, xc, Y, Z, Cc)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=feats.device)
+    elif tuple(out.shape) != shape or not out.is_contiguous():
+        raise ValueError("out must be a contiguous %s tensor" % (shape,))
+    idx = valid = gpos = None
+    if return_aux:
+        idx = torch.empty((B, V, xc, Y, Z, 2), dtype=torch.int32, device=feats.device)
+        valid = torch.empty((B, V, xc, Y, Z), dtype=torch.uint8, device=feats.device)
+    if world_grid:
+        gpos = torch.empty((B, 3), dtype=torch.float32, device=feats.device)
+    scale, shift = _bn_affine(bn, Cc, feats.device)
+    flags = (_lib.FLAG_RELU_IN if relu_in else 0) | (_lib.FLAG_RELU_OUT if relu_out else 0) | \
+            (_lib.FLAG_WORLD_GRID if world_grid else 0)
+    grid_dist = float(getattr(config, "GRID_DIST", 600 / 320 * config.vmax))
+    ih, iw = _image_hw(config)
+    rc = lib.mvf_unproject_fuse(_ptr(feats), _ptr(Rcam), _ptr(Rmain), _ptr(Kmat), C.byref(g), B, V, fh, fw, Cc,
+                                ih, iw, m, flags, grid_dist, xb, xc, _ptr(scale), _ptr(shift),
+                                _ptr(out), _ptr(idx), _ptr(valid), _ptr(gpos), _stream())
+    check(rc, "mvf_unproject_fuse")
+    res = (out,)
+    if world_grid:
+        res += (gpos,)
+    if return_aux:
+        res += (idx, valid)
+    return res[0] if len(res) == 1 else res
+
+
+def unproj_feat(inputs, config, return_aux=False):
+    """``unproj_feat([feats, Rcam, Kmat], config)`` -> [B,V,X,Y,Z,C]  (model_multi.py:130-228)."""
+    feats, Rcam, Kmat = inputs
+    return unproject_fuse(feats, Rcam, Kmat, config, mode="none", return_aux=return_aux)
+
+
+def unproj_feat_notebook(inputs, config, return_aux=False):
+    """World-frame variant, returns ``[grid, grid_position]`` (Notebook/projection.py:47-151)."""
+    feats, Rcam, Kmat = inputs
+    return unproject_fuse(feats, Rcam, Kmat, config, mode="none", world_grid=True, return_aux=return_aux)
+
+
+def view_reduce(x, mode, bn=None, relu_in=False, relu_out=False):
+    x = _cuda(x, "x")
+    if x.dim() != 6:
+        raise ValueError("expected [B,V,X,Y,Z,C]")
+    B, V, X, Y, Z, Cc = x.shape
+    out = torch.empty((B, X, Y, Z, Cc), dtype=torch.float32, device=x.device)
+    scale, shift = _bn_affine(bn, Cc, x.device)
+    flags = (_lib.FLAG_RELU_IN if relu_in else 0) | (_lib.FLAG_RELU_OUT if relu_out else 0)
+    rc = lib.mvf_view_reduce(_ptr(x), B, V, X * Y * Z, Cc, _FUSE[mode], flags, _ptr(scale), _ptr(shift), _ptr(out), _stream())
+    check(rc, "mvf_view_reduce")
+    return out
+
+
+def convlstm_step(x, h_prev, c_prev, W, bias, forget_bias=1.0, relu_in=False):
+    """One ``ConvLSTMCell.call`` (mrcnn/recurrent.py:442-479): returns (h, c)."""
+    x = _cuda(x, "x")
+    W = _cuda(W, "W")
+    bias = _cuda(bias, "bias")
+    B, X, Y, Z, Cc = x.shape
+    F = W.shape[-1] // 4
+    if tuple(W.shape) != (3, 3, 3, Cc + F, 4 * F):
+        raise ValueError("W must be [3,3,3,C+F,4F] (recurrent.py:423-426), got %s" % (tuple(W.shape),))
+    h = torch.empty((B, X, Y, Z, F), dtype=torch.float32, device=x.device)
+    c = torch.empty_like(h)
+    hp = _cuda(h_prev, "h_prev") if h_prev is not None else None
+    cp = _cuda(c_prev, "c_prev") if c_prev is not None else None
+    rc = lib.mvf_convlstm_step(_ptr(x), _ptr(hp), _ptr(cp), _ptr(W), _ptr(bias), float(forget_bias), B, X, Y, Z, Cc, F,
+                               _lib.FLAG_RELU_IN if relu_in else 0, _ptr(h), _ptr(c), _stream())
+    check(rc, "mvf_convlstm_step")
+    return h, c
+
+
+def convlstm(grid, name, kernel=(3, 3, 3), filters=32, params=None, relu_in=False):
+    """``convlstm(grid, name, kernel, filters)`` (model_multi.py:109-123): ConvRNN3D over the view
+    axis with zero initial state, last output only.  Weights: ``weights[name] = {'W','b'}``."""
+    grid = _cuda(grid, "grid")
+    if tuple(kernel) != (3, 3, 3):
+        raise ValueError("only the reference's 3x3x3 kernel is built")
+    p = params if params is not None else weights.get(name)
+    if p is None:
+        raise ValueError("no weights registered for ConvLSTM %r (set_weights(name, W=..., b=...))" % name)
+    if grid.shape[-1] != filters:
+        raise ValueError("initial state takes the input's channel count, so C must equal filters (recurrent.py:145-147)")
+    V = grid.shape[1]
+    h = c = None
+    for t in range(V):
+        h, c = convlstm_step(grid[:, t], h, c, p["W"], p["b"], 1.0, relu_in=relu_in)
+    return h
+
+
+def grid_reas(inputs, scope, config, kernel=(3, 3, 3), params=None):
+    """``grid_reas(inputs, scope, config)`` (model_multi.py:394-463) on a materialised
+    [B,V,X,Y,Z,C] tensor; modes add | mean | max | ident | lstm3d."""
+    x = _cuda(inputs, "inputs")
+    mode = config.GRID_REAS
+    p = params if params is not None else weights.get(scope, {})
+    Cc = x.shape[-1]
+    if mode == "add":
+        return view_reduce(x, "sum", bn=p.get("bn", _default_bn(Cc)), relu_out=True)
+    if mode in ("mean", "max"):
+        has_bn = "bn" in p
+        return view_reduce(x, mode, bn=p.get("bn"), relu_out=has_bn)
+    if mode == "ident":
+        B, V, X, Y, Z, _ = x.shape
+        Wt = _cuda(p["weight"], "weight")
+        Cout = Wt.shape[-1]
+        bias = _cuda(p["bias"], "bias")
+        scale, shift = _bn_affine(p.get("bn", _default_bn(Cout)), Cout, x.device)
+        out = torch.empty((B, X, Y, Z, Cout), dtype=torch.float32, device=x.device)
+        rc = lib.mvf_ident_fuse(_ptr(x), _ptr(Wt.reshape(V * Cc, Cout)), _ptr(bias), _ptr(scale), _ptr(shift),
+                                B, V, X * Y * Z, Cc, Cout, _ptr(out), _stream())
+        check(rc, "mvf_ident_fuse")
+        return out
+    if mode == "lstm3d":
+        h = convlstm(x, scope + "_convlstm3d", kernel=kernel, filters=config.TOP_DOWN_PYRAMID_SIZE,
+                     params={"W": p["W"], "b": p["b"]} if "W" in p else None, relu_in=True)
+        scale, shift = _bn_affine(p.get("bn", _default_bn(h.shape[-1])), h.shape[-1], h.device)
+        return _affine_relu(h, scale, shift)
+    raise ValueError("GRID_REAS=%r is not built (hot path: add, mean, max, ident, lstm3d)" % (mode,))
+
+
+def _affine_relu(h, scale, shift):
+    """BN affine + ReLU on [B,X,Y,Z,F] via the view-reduce kernel with V=1 (one launch, no torch math)."""
+    B = h.shape[0]
+    Cc = h.shape[-1]
+    out = torch.empty_like(h)
+    N = h.numel() // (B * Cc)
+    rc = lib.mvf_view_reduce(_ptr(h), B, 1, N, Cc, _lib.FUSE_SUM, _lib.FLAG_RELU_OUT, _ptr(scale), _ptr(shift), _ptr(out), _stream())
+    check(rc, "mvf_view_reduce")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def _as_hw(proj_size):
+    if isinstance(proj_size, (tuple, list)):
+        return int(proj_size[0]), int(proj_size[1])
+    return int(proj_size), int(proj_size)
+
+
+def _proj_common(grid, Rcam, Kmat, config, proj_size, view, x_slab, grid_pos):
+    grid = _cuda(grid, "grid")
+    Rcam = _cuda(Rcam, "Rcam")
+    Kmat = _cuda(Kmat, "Kmat")
+    if grid.dim() != 5 or Rcam.dim() != 4:
+        raise ValueError("expected grid [B,X,Y,Z,C], Rcam [B,V,3,4]")
+    B, Xs, Y, Z, Cc = grid.shape
+    g = grid_from_config(config)
+    xb, xc = (0, g.nvox) if x_slab is None else (int(x_slab[0]), int(x_slab[1]))
+    if (Xs, Y, Z) != (xc, g.nvox, g.nvox_z):
+        raise ValueError("grid %s does not match config/slab (%d,%d,%d)" % (tuple(grid.shape), xc, g.nvox, g.nvox_z))
+    Rview = Rcam[:, view].contiguous()
+    Rmain = Rcam[:, 0].contiguous() if view != 0 else None
+    ph, pw = _as_hw(proj_size)
+    flags = _lib.FLAG_WORLD_GRID if grid_pos is not None else 0
+    gp = _cuda(grid_pos, "grid_pos") if grid_pos is not None else None
+    grid_dist = float(getattr(config, "GRID_DIST", 600 / 320 * config.vmax))
+    return grid, Rview, Rmain, Kmat, gp, g, B, Cc, ph, pw, flags, grid_dist, xb, xc
+
+
+def proj_grid(inputs, config, proj_size, view=0, x_slab=None, return_aux=False, out=None):
+    """``proj_grid([grid, Rcam, Kmat], config, proj_size)`` -> [B,S,P,P,C]  (model_multi.py:231-322).
+    The notebook variant takes ``[grid, grid_pos, Rcam, Kmat]`` (Notebook/projection.py:253).
+    ``proj_size`` may be (ph, pw); ``view`` picks the camera the rays belong to (reference: 0)."""
+    if len(inputs) == 4:
+        grid, grid_pos, Rcam, Kmat = inputs
+    else:
+        (grid, Rcam, Kmat), grid_pos = inputs, None
+    grid, Rview, Rmain, Kmat, gp, g, B, Cc, ph, pw, flags, gd, xb, xc = _proj_common(
+        grid, Rcam, Kmat, config, proj_size, view, x_slab, grid_pos)
+    S = int(config.samples)
+    shape = (B, S, ph, pw, Cc)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=grid.device)
+    elif tuple(out.shape) != shape or not out.is_contiguous():
+        raise ValueError("out must be a contiguous %s tensor" % (shape,))
+    vox = valid = None
+    if return_aux:
+        vox = torch.empty((B, S, ph, pw, 3), dtype=torch.int32, device=grid.device)
+        valid = torch.empty((B, S, ph, pw), dtype=torch.uint8, device=grid.device)
+    rc = lib.mvf_project_rays(_ptr(grid), _ptr(Rview), _ptr(Rmain), _ptr(Kmat), _ptr(gp), C.byref(g), B, Cc,
+                              _image_hw(config)[0], ph, pw, S, flags, gd, xb, xc, _ptr(out), _ptr(vox), _ptr(valid), _stream())
+    check(rc, "mvf_project_rays")
+    return (out, vox, valid) if return_aux else out
+
+
+def _depth_params(name, params, S, device):
+    p = params if params is not None else weights.get(name)
+    if p is None:
+        raise ValueError("no weights registered for depth_sampling %r (set_weights(name, weight=[S], bias=..., bn=...))" % name)
+    w = torch.as_tensor(p["weight"], dtype=torch.float32, device=device).reshape(-1).contiguous()
+    if w.numel() != S:
+        raise ValueError("depth conv weight must have S=%d entries" % S)
+    bias = float(p.get("bias", 0.0))
+    gamma, beta, mean, var = (float(np.asarray(a).reshape(-1)[0]) for a in p.get("bn", (1.0, 0.0, 0.0, 1.0)))
+    inv = np.float32(np.float32(1.0) / np.sqrt(np.float32(var) + np.float32(BN_EPS))) * np.float32(gamma)
+    shift = np.float32(beta) - np.float32(mean) * inv
+    return w, bias, float(inv), float(shift)
+
+
+def depth_sampling(x, config, name, params=None):
+    """``depth_sampling(x, config, name)`` non-conv3d branch: [B,S,P,P,C] -> [B,P,P,C]
+    (model_multi.py:481-487).  Weights: ``{'weight' [S], 'bias', 'bn' (4 scalars)}``."""
+    if config.GRID_REAS == "conv3d":
+        raise ValueError("depth_sampling conv3d branch is not built (SURVEY.md section 8(f) rank 2)")
+    x = _cuda(x, "x")
+    B, S, P1, P2, Cc = x.shape
+    w, bias, inv, shift = _depth_params(name, params, S, x.device)
+    out = torch.empty((B, P1, P2, Cc), dtype=torch.float32, device=x.device)
+    rc = lib.mvf_depth_collapse(_ptr(x), B, S, P1 * P2, Cc, _ptr(w), bias, inv, shift, _lib.FLAG_RELU_OUT, _ptr(out), _stream())
+    check(rc, "mvf_depth_collapse")
+    return out
+
+
+def proj_grid_depth_sampling(inputs, config, proj_size, name, params=None, view=0, x_slab=None):
+    """Fused ``depth_sampling(proj_grid(...))``: the ray slices [B,S,P,P,C] are never written."""
+    grid, Rcam, Kmat = inputs
+    grid, Rview, Rmain, Kmat, gp, g, B, Cc, ph, pw, flags, gd, xb, xc = _proj_common(
+        grid, Rcam, Kmat, config, proj_size, view, x_slab, None)
+    S = int(config.samples)
+    w, bias, inv, shift = _depth_params(name, params, S, grid.device)
+    out = torch.empty((B, ph, pw, Cc), dtype=torch.float32, device=grid.device)
+    rc = lib.mvf_project_depth_collapse(_ptr(grid), _ptr(Rview), _ptr(Rmain), _ptr(Kmat), None, C.byref(g), B, Cc,
+                                        _image_hw(config)[0], ph, pw, S, flags | _lib.FLAG_RELU_OUT, gd, xb, xc,
+                                        _ptr(w), bias, inv, shift, _ptr(out), _stream())
+    check(rc, "mvf_project_depth_collapse")
+    return out
+
+
+def unproject_fuse_project(feats, Rcam, Kmat, config, proj_size, mode="sum", bn=None, relu_out=False,
+                           grid_out=None, out=None):
+    """The fused pipeline: unproj_feat -> grid_reas(sum|mean|max [+BN+ReLU]) -> proj_grid.
+    Two launches (K1, K3); returns (ray slices [B,S,P,P,C], fused grid [B,X,Y,Z,C])."""
+    fused = unproject_fuse(feats, Rcam, Kmat, config, mode=mode, bn=bn, relu_out=relu_out, out=grid_out)
+    rays = proj_grid([fused, Rcam, Kmat], config, proj_size, out=out)
+    return rays, fused
+
+
+# ------------------------------------------------------------------------------------------------
+class PyramidROIAlign:
+    """``PyramidROIAlign(pool_shape)([boxes, image_meta] + feature_maps)`` (model_multi.py:779-885)."""
+
+    def __init__(self, pool_shape, **kwargs):
+        self.pool_shape = tuple(pool_shape)
+
+    def __call__(self, inputs, return_levels=False):
+        return self.call(inputs, return_levels)
+
+    def call(self, inputs, return_levels=False):
+        boxes = _cuda(inputs[0], "boxes")
+        image_meta = inputs[1]
+        maps = [_cuda(m, "feature_map") for m in inputs[2:]]
+        if len(maps) != 4:
+            raise ValueError("PyramidROIAlign takes the four maps P2..P5")
+        # image_shape = parse_image_meta_graph(image_meta)['image_shape'][0]   (:812, meta columns 4:7)
+        meta0 = image_meta[0, 4:6]
+        ih, iw = (int(v) for v in (meta0.tolist() if isinstance(meta0, torch.Tensor) else meta0))
+        B, R, _ = boxes.shape
+        Cc = maps[0].shape[-1]
+        for m in maps:
+            if m.shape[0] != B or m.shape[-1] != Cc:
+                raise ValueError("feature maps must share batch and channel sizes")
+        ph, pw = self.pool_shape
+        out = torch.empty((B, R, ph, pw, Cc), dtype=torch.float32, device=boxes.device)
+        lv = torch.empty((B, R), dtype=torch.int32, device=boxes.device) if return_levels else None
+        ptrs = (C.c_void_p * 4)(*[m.data_ptr() for m in maps])
+        H = (C.c_int * 4)(*[m.shape[1] for m in maps])
+        W = (C.c_int * 4)(*[m.shape[2] for m in maps])
+        rc = lib.mvf_pyramid_roi_align(_ptr(boxes), ptrs, H, W, B, R, Cc, ih, iw, ph, pw, _ptr(out), _ptr(lv), _stream())
+        check(rc, "mvf_pyramid_roi_align")
+        return (out, lv) if return_levels else out
+
+    def compute_output_shape(self, input_shape):
+        return input_shape[0][:2] + self.pool_shape + (input_shape[2][-1],)
+
+
+def non_max_suppression(boxes, scores, max_output_size, iou_threshold, class_ids=None):
+    """``tf.image.non_max_suppression(boxes, scores, max_output_size, iou_threshold)`` ->
+    (keep int32 [max_output_size] padded with -1, count).  boxes [n,4] or batched [p,n,4]."""
+    boxes = _cuda(boxes, "boxes")
+    scores = _cuda(scores, "scores")
+    batched = boxes.dim() == 3
+    b3 = boxes if batched else boxes[None]
+    nprob, n, _ = b3.shape
+    cls = _cuda(class_ids, "class_ids", torch.int32) if class_ids is not None else None
+    keep = torch.empty((nprob, max_output_size), dtype=torch.int32, device=boxes.device)
+    count = torch.empty((nprob,), dtype=torch.int32, device=boxes.device)
+    nbytes = lib.mvf_nms_workspace_bytes(nprob, n)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=boxes.device)
+    rc = lib.mvf_nms(_ptr(b3), _ptr(scores), _ptr(cls), nprob, n, float(iou_threshold), int(max_output_size),
+                     int(max_output_size), _ptr(keep), _ptr(count), _ptr(ws), nbytes, _stream())
+    check(rc, "mvf_nms")
+    return (keep, count) if batched else (keep[0], count[0])
+
+
+def _refine_batched(rois, probs, deltas, windows, config, return_keep=False):
+    rois = _cuda(rois, "rois")
+    probs = _cuda(probs, "probs")
+    deltas = _cuda(deltas, "deltas")
+    windows = _cuda(windows, "windows")
+    B, N, K = probs.shape
+    max_inst = int(config.DETECTION_MAX_INSTANCES)
+    det = torch.empty((B, max_inst, 6), dtype=torch.float32, device=rois.device)
+    keep = torch.empty((B, max_inst), dtype=torch.int32, device=rois.device)
+    count = torch.empty((B,), dtype=torch.int32, device=rois.device)
+    nbytes = lib.mvf_refine_detections_workspace_bytes(B, N)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=rois.device)
+    std = (C.c_float * 4)(*[float(np.float32(v)) for v in np.asarray(config.BBOX_STD_DEV).reshape(-1)])
+    min_conf = float(np.float32(config.DETECTION_MIN_CONFIDENCE)) if config.DETECTION_MIN_CONFIDENCE else 0.0
+    rc = lib.mvf_refine_detections(_ptr(rois), _ptr(probs), _ptr(deltas), _ptr(windows), std, B, N, K, min_conf,
+                                   float(np.float32(config.DETECTION_NMS_THRESHOLD)), max_inst, _ptr(det), _ptr(keep),
+                                   _ptr(count), _ptr(ws), nbytes, _stream())
+    check(rc, "mvf_refine_detections")
+    return (det, keep, count) if return_keep else det
+
+
+def refine_detections_graph(rois, probs, deltas, window, config, return_keep=False):
+    """``refine_detections_graph(rois, probs, deltas, window, config)`` -> [max_inst, 6]
+    (model_multi.py:1119-1214).  One scene: rois [N,4], probs [N,K], deltas [N,K,4], window [4]."""
+    res = _refine_batched(rois[None], probs[None], deltas[None], _cuda(window, "window")[None], config, return_keep)
+    if return_keep:
+        return res[0][0], res[1][0], res[2][0]
+    return res[0]
+
+
+def norm_boxes_graph(boxes, shape):
+    """``norm_boxes_graph`` (model_multi.py:3390-3405) on host values (window normalisation)."""
+    h, w = np.float32(shape[0]), np.float32(shape[1])
+    scale = np.array([h, w, h, w], dtype=np.float32) - np.float32(1.0)
+    shift = np.array([0.0, 0.0, 1.0, 1.0], dtype=np.float32)
+    return ((np.asarray(boxes, dtype=np.float32) - shift) / scale).astype(np.float32)
+
+
+class DetectionLayer:
+    """``DetectionLayer(config)([rois, mrcnn_class, mrcnn_bbox, image_meta])`` -> [B, max_inst, 6]
+    (model_multi.py:1217-1258)."""
+
+    def __init__(self, config=None, **kwargs):
+        self.config = config
+
+    def __call__(self, inputs):
+        return self.call(inputs)
+
+    def call(self, inputs):
+        rois, mrcnn_class, mrcnn_bbox, image_meta = inputs
+        meta = image_meta.detach().cpu().numpy() if isinstance(image_meta, torch.Tensor) else np.asarray(image_meta)
+        image_shape = meta[0, 4:7]                                         # :1241
+        windows = norm_boxes_graph(meta[:, 7:11], image_shape[:2])         # :1242
+        wd = torch.as_tensor(windows, device=rois.device)
+        det = _refine_batched(rois, mrcnn_class, mrcnn_bbox, wd, self.config)
+        return det.reshape(self.config.BATCH_SIZE, self.config.DETECTION_MAX_INSTANCES, 6)
+
+    def compute_output_shape(self, input_shape):
+        return (None, self.config.DETECTION_MAX_INSTANCES, 6)
+
+
+class ProposalLayer:
+    """``ProposalLayer(proposal_count, nms_threshold, config)([rpn_probs, rpn_bbox, anchors])`` ->
+    [B, proposal_count, 4]  (model_multi.py:690-767)."""
+
+    def __init__(self, proposal_count, nms_threshold, config=None, **kwargs):
+        self.config = config
+        self.proposal_count = int(proposal_count)
+        self.nms_threshold = float(nms_threshold)
+
+    def __call__(self, inputs):
+        return self.call(inputs)
+
+    def call(self, inputs):
+        probs = _cuda(inputs[0], "rpn_probs")
+        bbox = _cuda(inputs[1], "rpn_bbox")
+        anchors = _cuda(inputs[2], "anchors")
+        B, A, _ = probs.shape
+        out = torch.empty((B, self.proposal_count, 4), dtype=torch.float32, device=probs.device)
+        count = torch.empty((B,), dtype=torch.int32, device=probs.device)
+        limit = int(self.config.PRE_NMS_LIMIT)
+        nbytes = lib.mvf_proposals_workspace_bytes(B, A, limit)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=probs.device)
+        std = (C.c_float * 4)(*[float(np.float32(v)) for v in np.asarray(self.config.RPN_BBOX_STD_DEV).reshape(-1)])
+        rc = lib.mvf_proposals(_ptr(probs), _ptr(bbox), _ptr(anchors), std, B, A, limit, self.proposal_count,
+                               float(np.float32(self.nms_threshold)), _ptr(out), _ptr(count), _ptr(ws), nbytes, _stream())
+        check(rc, "mvf_proposals")
+        return out
+
+    def compute_output_shape(self, input_shape):
+        return (None, self.proposal_count, 4)
+
+
+# ------------------------------------------------------------------------------------------------
+class HostPipeline:
+    """End-to-end entry over HOST buffers (the reference's only host->device crossing is
+    ``keras_model.predict``, model_multi.py:3067-3068): pinned feats/Rcam/Kmat in, pinned ray slices
+    out, device scratch owned by this object.  One call = H2D + K1 + K3 + D2H + stream sync."""
+
+    def __init__(self, config, B, V, fh, fw, Cc, proj_size, mode="sum", device=None):
+        self.config = config
+        self.g = grid_from_config(config)
+        self.shape = (B, V, fh, fw, Cc)
+        self.ph, self.pw = _as_hw(proj_size)
+        self.S = int(config.samples)
+        self.mode = _FUSE[mode]
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.nbytes = lib.mvf_pipeline_host_workspace_bytes(C.byref(self.g), B, V, fh, fw, Cc, self.ph, self.pw, self.S)
+        self.ws = torch.empty((self.nbytes,), dtype=torch.uint8, device=device)
+        self.h2d_bytes = 4 * (B * V * fh * fw * Cc + B * V * 12 + B * 9)
+        self.d2h_bytes = 4 * B * self.S * self.ph * self.pw * Cc
+
+    def empty_output(self):
+        B, _, _, _, Cc = self.shape
+        return torch.empty((B, self.S, self.ph, self.pw, Cc), dtype=torch.float32).pin_memory()
+
+    def __call__(self, h_feats, h_Rcam, h_Kmat, h_out):
+        for t, n in ((h_feats, "feats"), (h_Rcam, "Rcam"), (h_Kmat, "Kmat"), (h_out, "out")):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("%s must be a contiguous fp32 HOST tensor" % n)
+        B, V, fh, fw, Cc = self.shape
+        if tuple(h_feats.shape) != self.shape:
+            raise ValueError("feats shape %s != %s" % (tuple(h_feats.shape), self.shape))
+        ih, iw = _image_hw(self.config)
+        rc = lib.mvf_unproject_fuse_project_host(_ptr(h_feats), _ptr(h_Rcam), _ptr(h_Kmat), C.byref(self.g), B, V, fh, fw, Cc,
+                                                 ih, iw, self.mode, 0, None, None, self.ph, self.pw, self.S,
+                                                 _ptr(h_out), _ptr(self.ws), self.nbytes, _stream())
+        check(rc, "mvf_unproject_fuse_project_host")
+        return h_out

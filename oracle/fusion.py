@@ -1,0 +1,155 @@
+"""Oracle for view fusion ``grid_reas`` and the recurrent ConvLSTM voxel update
+(test infrastructure, see oracle/__init__.py).
+
+Restates mrcnn/model_multi.py:394-463 (``add``, ``ident``, ``lstm3d``), the notebook
+``mean`` (Notebook/projection.py:526-529) and mrcnn/recurrent.py:143-173,414-479.
+"""
+import numpy as np
+
+from .geometry import F32
+
+BN_EPS = 1e-3          # Keras BatchNormalization default epsilon (model_multi.py:501-502)
+
+
+def batch_norm_affine(gamma, beta, mean, var, eps=BN_EPS):
+    """Frozen-statistics BatchNorm as the affine ``x*scale + shift`` that
+    ``tf.nn.batch_normalization`` evaluates: ``inv = rsqrt(var+eps)*gamma``,
+    ``shift = beta - mean*inv`` (TRAIN_BN=False, mrcnn/config.py:208)."""
+    gamma, beta, mean, var = (np.asarray(a, dtype=F32) for a in (gamma, beta, mean, var))
+    inv = (F32(1.0) / np.sqrt(var + F32(eps))).astype(F32) * gamma
+    shift = beta - mean * inv
+    return inv.astype(F32), shift.astype(F32)
+
+
+def fuse_views(grids, mode):
+    """Reduce [B,V,X,Y,Z,C] over the view axis.
+
+    ``sum``  : ``K.sum(x, axis=1)`` (model_multi.py:402), evaluated in ascending v.
+    ``mean`` : ``sum * float32(1/V)``         -- defined by this oracle (parity unpinned:
+    ``max``  : ``max_v`` of the zero-filled      the reference has neither, SURVEY.md spec B).
+               per-view samples, ascending v"""
+    grids = np.asarray(grids, dtype=F32)
+    V = grids.shape[1]
+    acc = grids[:, 0].copy()
+    if mode in ("sum", "add", "mean"):
+        for v in range(1, V):
+            acc = acc + grids[:, v]
+        if mode == "mean":
+            acc = acc * F32(F32(1.0) / F32(V))
+    elif mode == "max":
+        for v in range(1, V):
+            acc = np.maximum(acc, grids[:, v])
+    else:
+        raise ValueError(mode)
+    return acc.astype(F32)
+
+
+def channel_mean(grids):
+    """The notebook's ``GRID_REAS='mean'`` (Notebook/projection.py:526-529,549): the mean is
+    taken over the CHANNEL axis and the V per-view scalars become the channels, then ReLU.
+    [B,V,X,Y,Z,C] -> [B,X,Y,Z,V]."""
+    grids = np.asarray(grids, dtype=F32)
+    C = grids.shape[-1]
+    acc = grids[..., 0].copy()
+    for c in range(1, C):
+        acc = acc + grids[..., c]
+    m = acc / F32(C)
+    return np.maximum(np.transpose(m, (0, 2, 3, 4, 1)), F32(0)).astype(F32)
+
+
+def ident_fuse(grids, weight, bias, bn):
+    """``GRID_REAS='ident'`` (model_multi.py:443-455): ReLU -> concat views on the channel
+    axis (view-major: v*C + c) -> Conv3D 1x1x1 (+bias) -> BN -> ReLU.
+    weight [V*C, Cout] (the [1,1,1,V*C,Cout] Keras kernel squeezed), bias [Cout],
+    bn = (scale, shift) from :func:`batch_norm_affine`.  Contraction accumulated in float64
+    and rounded once (conv summation order is not observable; compare with a tolerance)."""
+    grids = np.asarray(grids, dtype=F32)
+    B, V, X, Y, Z, C = grids.shape
+    x = np.maximum(grids, F32(0))
+    x = np.transpose(x, (0, 2, 3, 4, 1, 5)).reshape(B, X, Y, Z, V * C)
+    y = (x.astype(np.float64) @ np.asarray(weight, dtype=np.float64)).astype(F32)
+    y = y + np.asarray(bias, dtype=F32)
+    scale, shift = bn
+    return np.maximum(y * scale + shift, F32(0)).astype(F32)
+
+
+def _sigmoid(x):
+    x = x.astype(np.float64)
+    return (1.0 / (1.0 + np.exp(-x)))
+
+
+def conv3d_same(x, W):
+    """``tf.nn.convolution(x, W, 'SAME')`` for a [B,X,Y,Z,Cin] input and a [kx,ky,kz,Cin,Cout]
+    filter, stride 1, zero padding (recurrent.py:457).  float64 accumulation."""
+    x = np.asarray(x, dtype=np.float64)
+    W = np.asarray(W, dtype=np.float64)
+    B, X, Y, Z, Cin = x.shape
+    kx, ky, kz, _, Cout = W.shape
+    px, py, pz = kx // 2, ky // 2, kz // 2
+    xp = np.zeros((B, X + kx - 1, Y + ky - 1, Z + kz - 1, Cin))
+    xp[:, px:px + X, py:py + Y, pz:pz + Z] = x
+    y = np.zeros((B, X, Y, Z, Cout))
+    for a in range(kx):
+        for b_ in range(ky):
+            for c in range(kz):
+                y += xp[:, a:a + X, b_:b_ + Y, c:c + Z] @ W[a, b_, c]
+    return y
+
+
+def convlstm_cell_step(x, c_prev, h_prev, W, bias, forget_bias=1.0):
+    """One ``ConvLSTMCell.call`` (mrcnn/recurrent.py:442-479, normalize=False):
+    ``y = conv3d_SAME([x ; h_prev], W) + b``; gates split in the order
+    ``j, i, f, o`` (:460-461); ``c = c_prev*sigmoid(f + forget_bias) + sigmoid(i)*tanh(j)``;
+    ``h = tanh(c)*sigmoid(o)`` (:470-477).  Returns (h, c) as fp32."""
+    xin = np.concatenate([np.asarray(x, F32), np.asarray(h_prev, F32)], axis=-1)
+    y = conv3d_same(xin, W) + np.asarray(bias, dtype=np.float64)
+    j, i, f, o = np.split(y, 4, axis=-1)
+    c = np.asarray(c_prev, np.float64) * _sigmoid(f + forget_bias) + _sigmoid(i) * np.tanh(j)
+    h = np.tanh(c) * _sigmoid(o)
+    return h.astype(F32), c.astype(F32)
+
+
+def convlstm(grids, W, bias, forget_bias=1.0):
+    """``convlstm(grid, name, kernel, filters)`` (model_multi.py:109-123) = ``ConvRNN3D`` over
+    the view axis with zero initial states shaped like the input (recurrent.py:143-173, so
+    C == F), returning the last output only (return_sequences=False)."""
+    grids = np.asarray(grids, dtype=F32)
+    B, V, X, Y, Z, C = grids.shape
+    F = W.shape[-1] // 4
+    assert C == F, "initial state takes the input's channel count (recurrent.py:145-147)"
+    c = np.zeros((B, X, Y, Z, F), F32)
+    h = np.zeros((B, X, Y, Z, F), F32)
+    for t in range(V):
+        h, c = convlstm_cell_step(grids[:, t], c, h, W, bias, forget_bias)
+    return h
+
+
+def grid_reas(grids, scope, cfg, params=None):
+    """``grid_reas(inputs, scope, config)`` (model_multi.py:394-463) for the modes on the hot
+    path.  ``params`` carries the frozen learnables of ``scope``:
+      add    : {'bn': (gamma,beta,mean,var)}
+      ident  : {'weight' [V*C,Cout], 'bias' [Cout], 'bn': ...}
+      lstm3d : {'W' [3,3,3,C+F,4F], 'b' [4F], 'bn': ...}
+      mean / max (oracle-defined, no BN in the reference): optional 'bn'."""
+    params = params or {}
+    mode = cfg.GRID_REAS
+    bn = batch_norm_affine(*params["bn"]) if "bn" in params else None
+    if mode == "add":
+        x = fuse_views(grids, "sum")                            # :402
+        if bn is not None:
+            x = x * bn[0] + bn[1]                               # :403
+        return np.maximum(x, F32(0)).astype(F32)                # :404
+    if mode in ("mean", "max"):
+        x = fuse_views(grids, mode)
+        if bn is not None:
+            x = np.maximum(x * bn[0] + bn[1], F32(0))
+        return x.astype(F32)
+    if mode == "ident":
+        return ident_fuse(grids, params["weight"], params["bias"], bn)
+    if mode == "lstm3d":
+        x = np.maximum(np.asarray(grids, F32), F32(0))          # :459
+        h = convlstm(x, params["W"], params["b"])               # :460
+        if bn is not None:
+            h = h * bn[0] + bn[1]                               # :461
+        return np.maximum(h, F32(0)).astype(F32)                # :462
+    raise ValueError("GRID_REAS=%r is not on the hot path" % (mode,))
