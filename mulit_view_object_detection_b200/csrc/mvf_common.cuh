@@ -69,6 +69,22 @@ __device__ __forceinline__ float4 max4(float4 a, float4 b) { return make_float4(
 __device__ __forceinline__ float4 relu4(float4 a) { return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 issues two fp32 FMAs per instruction slot) ---------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 dup2(float w) { u64 d; asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(w)); return d; }   // folds into FFMA2's scalar operand
+__device__ __forceinline__ u64 pack2(float a, float b) { u64 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float2 unpack2(u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ ulonglong2 ldg2x2(const void* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); }
+// acc + w * t for four channels held as two packed pairs
+__device__ __forceinline__ ulonglong2 fma2x2(float w, ulonglong2 t, ulonglong2 a) {
+    const u64 ww = dup2(w);
+    a.x = fma2(t.x, ww, a.x); a.y = fma2(t.y, ww, a.y);
+    return a;
+}
+__device__ __forceinline__ float4 unpack4(ulonglong2 v) { const float2 a = unpack2(v.x), b = unpack2(v.y); return make_float4(a.x, a.y, b.x, b.y); }
+__device__ __forceinline__ ulonglong2 pack4(float4 v) { ulonglong2 r; r.x = pack2(v.x, v.y); r.y = pack2(v.z, v.w); return r; }
+
 // ---- host: TF1 RangeOp<float> / LinSpaceOp<float> fill order ---------------------------------
 // (third-party kernels restated; call sites mrcnn/model_multi.py:157-160, :267)
 inline int tf1_range(double start_d, double limit_d, double delta_d, float* out, int cap) {

@@ -4,7 +4,12 @@
 // world-frame notebook variant Notebook/projection.py:47-151.  The per-view grids
 // [B,V,X,Y,Z,C] are never materialised unless mode == MVF_FUSE_NONE.
 //
-// Mapping: one CTA = one 4x4x16 brick of voxels of one scene; a warp owns 32 voxels of the
+// Two kernels live here.  The production kernel is unproject_run_kernel (further down): a warp
+// owns a z-run of one voxel column and caches the bilinear 2x2 patch in registers.  The first
+// generation brick kernel below is kept for A/B measurement (MVF_K1_VARIANT=0) and for V > 1
+// shapes the run kernel does not cover.
+//
+// Brick kernel mapping: one CTA = one 4x4x16 brick of voxels of one scene; a warp owns 32 voxels of the
 // brick.  Lanes first work as 32 independent (voxel, view) coordinate units -- voxel->pixel
 // projection, floor, the four weights and the tap-validity bits are computed ONCE per pair in
 // registers with individually rounded fp32 ops (bit-exact against the oracle) -- and then the
@@ -13,6 +18,7 @@
 // (512 B per warp instruction) and every voxel one coalesced streaming 128-bit store.
 // The view reduction lives in the accumulator registers.
 #include "mvf_common.cuh"
+#include <stdlib.h>
 
 namespace mvf {
 
@@ -215,6 +221,260 @@ unproject_fuse_kernel(const __grid_constant__ UnprojParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Run kernel (production).  A warp owns L consecutive z-voxels of ONE (ix,iy) column for ONE
+// chunk of 128*CPL channels.  All L accumulators stay in registers across the whole view loop
+// (the per-view grids never exist), and the four taps of the current bilinear cell are cached in
+// registers: along a z-run the projected pixel moves ~0.3 px per voxel, so only about one step in
+// three changes cell and has to touch the load pipe at all.  On-chip load bandwidth (128 B/clk/SM
+// through L1), not HBM, is what bounds this op, so cutting tap loads is the lever.
+//   phase A (lanes = (view, z-step) pairs): voxel->pixel projection, floor, weights, validity and
+//           the "cell changed" flag, individually rounded fp32 (bit-exact vs the oracle), written
+//           to a 32-slot per-warp shared-memory table;
+//   phase B (lanes = float4 channel slots): walk the run; per step one broadcast LDS.128 of the
+//           four weights, a predicated patch reload (4 coalesced 128-bit read-only loads, 512 B
+//           per warp instruction) when the cell changed, and 16 FMAs straight into the accumulators.
+constexpr int RUN_WARPS = 8, RUN_TX = 4, RUN_TY = 2;
+
+// FULLC: C/4 is a multiple of 32*CPL, so no lane ever falls off the channel vector.
+template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC>
+__global__ void __launch_bounds__(RUN_WARPS * 32)
+unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
+    constexpr int VPP = 32 / L;                       // views handled per phase A
+    static_assert(VPP * L == 32, "L must divide 32");
+    __shared__ float sKR[MVF_MAX_VIEWS][12];
+    __shared__ float sOff[3];
+    __shared__ __align__(16) float4 sW[RUN_WARPS][32];   // the four bilinear weights (0 for an out-of-map tap)
+    __shared__ __align__(16) uint4 sO[RUN_WARPS][32];    // the four tap BYTE offsets inside a view (clamped into the map)
+
+    const int b = blockIdx.y / nchunk, chunk = blockIdx.y - b * nchunk;
+    const int tid = threadIdx.x;
+    const bool world = (p.flags & MVF_FLAG_WORLD_GRID) != 0;
+    if (tid < p.V) {
+        const float* P = p.Rcam + ((size_t)b * p.V + tid) * 12;
+        const float* K = p.Kmat + (size_t)b * 9;
+        const float* P0 = p.Rmain ? p.Rmain + (size_t)b * 12 : p.Rcam + (size_t)b * p.V * 12;
+        float Rinv[12], M[12];
+        inverse_pose(P, Rinv);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                M[i * 4 + j] = dot3_rn(K[i * 3 + 0], K[i * 3 + 1], K[i * 3 + 2],
+                                       Rinv[0 * 4 + j], Rinv[1 * 4 + j], Rinv[2 * 4 + j]);
+        if (world) {
+#pragma unroll
+            for (int e = 0; e < 12; ++e) sKR[tid][e] = M[e];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float t3 = (j == 3) ? 1.0f : 0.0f;
+                    sKR[tid][i * 4 + j] = dot4_rn(M[i * 4 + 0], M[i * 4 + 1], M[i * 4 + 2], M[i * 4 + 3],
+                                                  P0[0 * 4 + j], P0[1 * 4 + j], P0[2 * 4 + j], t3);
+                }
+        }
+    }
+    if (tid == 32 && world) {
+        const float* P0 = p.Rmain ? p.Rmain + (size_t)b * 12 : p.Rcam + (size_t)b * p.V * 12;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float v = dot4_rn(P0[i * 4 + 0], P0[i * 4 + 1], P0[i * 4 + 2], P0[i * 4 + 3], 0.0f, 0.0f, p.grid_dist, 1.0f);
+            sOff[i] = v;
+            if (p.out_grid_pos && blockIdx.x == 0 && chunk == 0) p.out_grid_pos[b * 3 + i] = v;
+        }
+    }
+    __syncthreads();
+
+    const int tiles_z = (p.Z + L - 1) / L;
+    const int tiles_y = (p.Y + RUN_TY - 1) / RUN_TY;
+    int t = blockIdx.x;
+    const int tz = t % tiles_z; t /= tiles_z;
+    const int ty = t % tiles_y; t /= tiles_y;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ixs = t * RUN_TX + (warp % RUN_TX);
+    const int iy = ty * RUN_TY + (warp / RUN_TX);
+    const int z0 = tz * L;
+    if (ixs >= p.Xs || iy >= p.Y) return;             // warp-uniform; no block-wide sync below
+    const unsigned FULL = 0xffffffffu;
+
+    const int C = p.C, V = p.V, C4 = C >> 2;
+    const size_t view_stride = (size_t)p.fh * p.fw * C;
+    const int c4base = chunk * 32 * CPL + lane;
+    // lane's channel slot(s); a slot past the end of the channel vector re-reads the last one and
+    // is dropped at the store
+    unsigned lane_off[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) lane_off[c] = 16u * (unsigned)(FULLC ? (c4base + 32 * c) : min(c4base + 32 * c, C4 - 1));
+    const float* feats_b = p.feats + (size_t)b * V * view_stride;
+
+    float gxv = p.gx[p.x_begin + ixs], gyv = p.gy[iy];
+    if (world) { gxv = add_rn(gxv, sOff[0]); gyv = add_rn(gyv, sOff[1]); }
+
+    // accumulators and the cached bilinear patch live as packed fp32x2 pairs (FFMA2 operands)
+    const ulonglong2 zz = make_ulonglong2(0ull, 0ull);
+    ulonglong2 acc[L][CPL];
+#pragma unroll
+    for (int k = 0; k < L; ++k)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc[k][c] = zz;
+    // the patch stays finite (zero or real features), so a zero weight always contributes 0
+    ulonglong2 tA[CPL], tB[CPL], tC[CPL], tD[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) { tA[c] = zz; tB[c] = zz; tC[c] = zz; tD[c] = zz; }
+
+    for (int v0 = 0; v0 < V; v0 += VPP) {
+        // ---- phase A: lane = (view v0 + lane / L, z-step lane % L)
+        unsigned rmask;
+        {
+            const int sub = lane / L, k = lane - sub * L;
+            const int v = v0 + sub, iz = z0 + k;
+            float wa = 0.f, wb = 0.f, wc = 0.f, wd = 0.f;
+            uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
+            int bits = 0, x0 = INT32_MIN, y0 = INT32_MIN;
+            if (v < V && iz < p.Z) {
+                float z = p.gz[iz];
+                if (world) z = add_rn(z, sOff[2]);
+                const float* KR = sKR[v];
+                const float px = affine_row(KR, 0, gxv, gyv, z);
+                const float py = affine_row(KR, 1, gxv, gyv, z);
+                const float pz = affine_row(KR, 2, gxv, gyv, z);
+                const float u = mul_rn(div_rn(px, pz), p.sx);               // :187
+                const float w = mul_rn(div_rn(py, pz), p.sy);               // :188
+                if (usable_coord(u) && usable_coord(w)) {
+                    const float x0f = floorf(u), y0f = floorf(w);            // :192-195
+                    x0 = (int)x0f; y0 = (int)y0f;
+                    const float x1f = (float)(x0 + 1), y1f = (float)(y0 + 1);
+                    const float ax = sub_rn(x1f, u), bx = sub_rn(u, x0f);
+                    const float ay = sub_rn(y1f, w), by = sub_rn(w, y0f);
+                    const bool inx0 = (x0 >= 0) && (x0 < p.fw), inx1 = (x0 + 1 >= 0) && (x0 + 1 < p.fw);
+                    const bool iny0 = (y0 >= 0) && (y0 < p.fh), iny1 = (y0 + 1 >= 0) && (y0 + 1 < p.fh);
+                    bits = (int)(iny0 && inx0) | ((int)(iny1 && inx0) << 1) | ((int)(iny0 && inx1) << 2) |
+                           ((int)(iny1 && inx1) << 3);
+                    if (bits) {
+                        // weights of the reference (:214-217); an out-of-map tap reads 0 there (TF-GPU gather_nd),
+                        // here its weight is zeroed and its address clamped into the map instead
+                        wa = (bits & 1) ? mul_rn(ax, ay) : 0.f; wb = (bits & 2) ? mul_rn(ax, by) : 0.f;
+                        wc = (bits & 4) ? mul_rn(bx, ay) : 0.f; wd = (bits & 8) ? mul_rn(bx, by) : 0.f;
+                        const int xa = min(max(x0, 0), p.fw - 1), xb = min(max(x0 + 1, 0), p.fw - 1);
+                        const int ya = min(max(y0, 0), p.fh - 1), yb = min(max(y0 + 1, 0), p.fh - 1);
+                        const unsigned CB = 4u * (unsigned)C;
+                        const unsigned oa = (unsigned)(ya * p.fw + xa) * CB;
+                        const unsigned dX = (xb != xa) ? CB : 0u, dY = (yb != ya) ? (unsigned)p.fw * CB : 0u;
+                        o4 = make_uint4(oa, oa + dY, oa + dX, oa + dX + dY);
+                    }
+                }
+                if (chunk == 0 && (p.out_idx || p.out_valid)) {
+                    const size_t vox = (((size_t)b * V + v) * p.Xs + ixs) * p.Y * p.Z + (size_t)iy * p.Z + iz;
+                    if (p.out_idx) { p.out_idx[vox * 2 + 0] = y0; p.out_idx[vox * 2 + 1] = x0; }
+                    if (p.out_valid) p.out_valid[vox] = (uint8_t)bits;
+                }
+            }
+            // the patch is (re)loaded when this step samples a cell that differs from the previous
+            // step's (or follows a step that sampled nothing)
+            const int px0 = __shfl_up_sync(FULL, x0, 1), py0 = __shfl_up_sync(FULL, y0, 1);
+            const int pbits = __shfl_up_sync(FULL, bits, 1);
+            const bool reload = (bits != 0) && (k == 0 || pbits == 0 || px0 != x0 || py0 != y0);
+            rmask = __ballot_sync(FULL, reload);
+            sW[warp][lane] = make_float4(wa, wb, wc, wd);
+            sO[warp][lane] = o4;
+        }
+        __syncwarp();
+        // ---- phase B: lanes = float4 channel slots
+#pragma unroll
+        for (int sub = 0; sub < VPP; ++sub) {
+            const int vv = v0 + sub;
+            if (vv >= V) break;
+            // per-lane 64-bit base of this view; a tap address is base + (warp-uniform 32-bit byte offset)
+            const char* vb[CPL];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) vb[c] = (const char*)(feats_b + (size_t)vv * view_stride) + lane_off[FULLC ? 0 : c];
+#pragma unroll
+            for (int k = 0; k < L; ++k) {
+                const int slot = sub * L + k;
+                if ((rmask >> slot) & 1u) {                                // warp-uniform
+                    const uint4 o = sO[warp][slot];                        // broadcast LDS.128
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) {
+                        const char* q = FULLC ? vb[0] + 512 * c : vb[c];
+                        tA[c] = ldg2x2(q + o.x); tB[c] = ldg2x2(q + o.y); tC[c] = ldg2x2(q + o.z); tD[c] = ldg2x2(q + o.w);
+                    }
+                }
+                const float4 w = sW[warp][slot];                           // broadcast LDS.128
+                if (MODE != MVF_FUSE_NONE && MODE != MVF_FUSE_MAX && !RELU_IN) {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c)                          // 8 FFMA2 = 16 fp32 FMAs
+                        acc[k][c] = fma2x2(w.w, tD[c], fma2x2(w.z, tC[c], fma2x2(w.y, tB[c], fma2x2(w.x, tA[c], acc[k][c]))));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) {
+                        float4 val = unpack4(fma2x2(w.w, tD[c], fma2x2(w.z, tC[c], fma2x2(w.y, tB[c], fma2x2(w.x, tA[c], zz)))));
+                        if (RELU_IN) val = relu4(val);
+                        if (MODE == MVF_FUSE_NONE) {
+                            if (z0 + k < p.Z && (FULLC || c4base + 32 * c < C4)) {
+                                float* o = p.out + ((((size_t)b * V + vv) * p.Xs + ixs) * p.Y * p.Z + (size_t)iy * p.Z + z0 + k) * C;
+                                stcs4(o + 4 * (c4base + 32 * c), val);
+                            }
+                        } else if (MODE == MVF_FUSE_MAX) {
+                            acc[k][c] = (vv == 0) ? pack4(val) : pack4(max4(unpack4(acc[k][c]), val));
+                        } else {
+                            acc[k][c] = pack4(add4(unpack4(acc[k][c]), val));
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (MODE == MVF_FUSE_NONE) return;
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+        if (z0 + k >= p.Z) break;
+        float* o = p.out + ((((size_t)b * p.Xs + ixs) * p.Y + iy) * p.Z + z0 + k) * C;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int c4 = c4base + 32 * c;
+            if (!FULLC && c4 >= C4) continue;
+            float4 r = unpack4(acc[k][c]);
+            if (MODE == MVF_FUSE_MEAN) r = mul4(p.inv_v, r);
+            if (p.bn_scale) {
+                const float4 s = ldg4(p.bn_scale + 4 * c4), h = ldg4(p.bn_shift + 4 * c4);
+                r = make_float4(fmaf(r.x, s.x, h.x), fmaf(r.y, s.y, h.y), fmaf(r.z, s.z, h.z), fmaf(r.w, s.w, h.w));
+            }
+            if (p.flags & MVF_FLAG_RELU_OUT) r = relu4(r);
+            stcs4(o + 4 * c4, r);
+        }
+    }
+}
+
+template <int CPL, int L, bool RELU_IN, bool FULLC>
+static int launch_run_mode(const UnprojParams& p, dim3 grid, int nchunk, cudaStream_t s) {
+    switch (p.mode) {
+        case MVF_FUSE_NONE: unproject_run_kernel<CPL, L, MVF_FUSE_NONE, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk); break;
+        case MVF_FUSE_SUM:  unproject_run_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk); break;
+        case MVF_FUSE_MEAN: unproject_run_kernel<CPL, L, MVF_FUSE_MEAN, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk); break;
+        case MVF_FUSE_MAX:  unproject_run_kernel<CPL, L, MVF_FUSE_MAX, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk); break;
+        default: return MVF_EINVAL;
+    }
+    count_launch();
+    return check_launch();
+}
+
+template <int CPL, int L>
+static int launch_run(const UnprojParams& p, int B, cudaStream_t s) {
+    const int C4 = p.C / 4;
+    const int nchunk = (C4 + 32 * CPL - 1) / (32 * CPL);
+    if ((long long)B * nchunk > 65535) return MVF_EUNSUPPORTED;
+    const int tiles = ((p.Xs + RUN_TX - 1) / RUN_TX) * ((p.Y + RUN_TY - 1) / RUN_TY) * ((p.Z + L - 1) / L);
+    dim3 grid(tiles, B * nchunk);
+    const bool fullc = (C4 % (32 * CPL)) == 0;
+    const bool relu_in = (p.flags & MVF_FLAG_RELU_IN) != 0;
+    if (fullc) return relu_in ? launch_run_mode<CPL, L, true, true>(p, grid, nchunk, s) : launch_run_mode<CPL, L, false, true>(p, grid, nchunk, s);
+    return relu_in ? launch_run_mode<CPL, L, true, false>(p, grid, nchunk, s) : launch_run_mode<CPL, L, false, false>(p, grid, nchunk, s);
+}
+
 template <int CPL>
 static int launch_k1(const UnprojParams& p, dim3 grid, cudaStream_t s) {
     switch (p.mode) {
@@ -260,7 +520,7 @@ extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const f
     if (C % 4 != 0 || !aligned16(feats) || !aligned16(out) || (bn_scale && (!aligned16(bn_scale) || !aligned16(bn_shift))))
         return MVF_EALIGN;
     if (V > MVF_MAX_VIEWS || C > 1024 || B > 65535) return MVF_EUNSUPPORTED;
-    if ((size_t)fh * fw * C >= (size_t)1 << 31) return MVF_EUNSUPPORTED;
+    if ((size_t)fh * fw * C >= (size_t)1 << 30) return MVF_EUNSUPPORTED;   // byte offsets inside a view fit 32 bits
     UnprojParams p;
     int rc = fill_centres(g, flags, p.gx, p.gy, p.gz);
     if (rc != MVF_OK) return rc;
@@ -281,6 +541,12 @@ extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const f
     dim3 grid(tiles, B);
     cudaStream_t s = (cudaStream_t)stream;
     const int C4 = C / 4;
+    // MVF_K1_VARIANT (debug / A-B measurement): 0 = first-generation brick kernel, 1 = run kernel
+    // 128 ch x 16 z-steps per warp (default), 2 = run kernel 256 ch x 8 z-steps, 3 = 128 ch x 8 z-steps.
+    static const int variant = [] { const char* e = getenv("MVF_K1_VARIANT"); return e ? atoi(e) : 1; }();
+    if (variant == 1) return launch_run<1, 16>(p, B, s);
+    if (variant == 2) return launch_run<2, 8>(p, B, s);
+    if (variant == 3) return launch_run<1, 8>(p, B, s);
     if (C4 <= 32) return launch_k1<1>(p, grid, s);
     if (C4 <= 64) return launch_k1<2>(p, grid, s);
     if (C4 <= 128) return launch_k1<4>(p, grid, s);

@@ -1,0 +1,206 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by EXECUTING THE REFERENCE'S OWN PYTHON.
+
+Run in the build container only (needs /root/reference; the GPU box never runs this):
+
+    python tests/golden/make_golden.py
+
+mrcnn/utils.py, mrcnn/recurrent.py and mrcnn/model_multi.py are imported unmodified from
+/root/reference over the eager NumPy ``tf``/``keras`` stand-in in tf1_shim.py, then the hot-path
+functions are called on small seeded inputs and inputs + outputs are stored as .npz files.
+tests/test_golden.py checks the oracle (CPU) and tests/test_gpu_golden.py the CUDA kernels against
+these files.  Fixtures are small (a few hundred KB in total).
+"""
+import io
+import os
+import sys
+import contextlib
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import tf1_shim  # noqa: E402
+
+tf = tf1_shim.install()
+sys.path.insert(0, REF)
+with contextlib.redirect_stdout(io.StringIO()):
+    from mrcnn import utils as ref_utils          # noqa: E402
+    from mrcnn import model_multi as mm           # noqa: E402
+
+from mulit_view_object_detection_b200.config import FusionConfig   # noqa: E402
+from mulit_view_object_detection_b200 import synthetic as syn      # noqa: E402
+
+T = tf1_shim.T
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def arr(x):
+    return np.array(np.asarray(x).view(np.ndarray))
+
+
+def save(name, **kw):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **kw)
+    print("wrote %-28s %6.1f KB" % (name + ".npz", os.path.getsize(path) / 1024.0))
+
+
+def cfg_dict(cfg, keys):
+    return {"cfg_" + k: np.asarray(getattr(cfg, k)) for k in keys}
+
+
+GRID_KEYS = ["nvox", "nvox_z", "vmin", "vmax", "vsize", "vmin_z", "vmax_z", "vsize_z", "samples", "IMAGE_SHAPE",
+             "IMAGES_PER_GPU", "NUM_VIEWS"]
+
+
+def gen_unproject_project():
+    cases = [
+        ("fusion_a", dict(nvox=6, nvox_z=5, samples=4, NUM_VIEWS=3, IMAGES_PER_GPU=2), 12, 12, 4, 8),
+        # voxel sizes that are NOT exactly representable: exercises the sequential tf.range fill
+        ("fusion_b", dict(nvox=7, nvox_z=9, vmin=-2.5, vmax=2.5, vmin_z=1.0, vmax_z=10.0, samples=5, NUM_VIEWS=2,
+                          IMAGES_PER_GPU=1), 10, 14, 8, 10),
+    ]
+    for name, kw, fh, fw, C, P in cases:
+        cfg = FusionConfig(**kw)
+        B, V = cfg.BATCH_SIZE, cfg.NUM_VIEWS
+        feats, Rcam, Kmat = syn.make_scene(cfg, B, V, fh, fw, C, seed=zlib.crc32(name.encode()) % 1000)
+        per_view = quiet(mm.unproj_feat, [T(feats), T(Rcam), T(Kmat)], cfg)
+        summed = tf.keras.backend.sum(per_view, axis=1)                       # grid_reas 'add', model_multi.py:402
+        rays = quiet(mm.proj_grid, [summed, T(Rcam), T(Kmat)], cfg, P)
+        save(name, feats=feats, Rcam=Rcam, Kmat=Kmat, proj_size=np.int32(P), per_view=arr(per_view), summed=arr(summed),
+             rays=arr(rays), **cfg_dict(cfg, GRID_KEYS))
+
+
+def gen_boxes():
+    rng = np.random.default_rng(11)
+    boxes = syn.make_rois(rng, 1, 64, pad_frac=0.1)[0]
+    deltas = rng.normal(0, 0.5, (64, 4)).astype(np.float32)
+    window = np.array([0.1, 0.05, 0.9, 1.0], np.float32)
+    applied = mm.apply_box_deltas_graph(T(boxes), T(deltas))
+    clipped = mm.clip_boxes_graph(applied, T(window))
+    # the reference's NumPy twins (mrcnn/utils.py) on the same inputs, for cross-reading
+    np_applied = ref_utils.apply_box_deltas(boxes.astype(np.float64), deltas.astype(np.float64))
+    save("boxes", boxes=boxes, deltas=deltas, window=window, applied=arr(applied), clipped=arr(clipped),
+         utils_applied_f64=np_applied)
+
+
+def gen_nms_utils():
+    """mrcnn/utils.py:381-415 non_max_suppression / :319-337 compute_iou -- pure NumPy, run unmodified."""
+    rng = np.random.default_rng(12)
+    n = 300
+    c = rng.uniform(0.2, 0.8, (n, 2))
+    s = rng.uniform(0.05, 0.3, (n, 2))
+    boxes = np.concatenate([c - s / 2, c + s / 2], axis=1).astype(np.float32)
+    scores = (rng.permutation(n).astype(np.float32) + 1) / n
+    out = {}
+    for thr in (0.3, 0.5, 0.7):
+        out["keep_%02d" % int(thr * 10)] = ref_utils.non_max_suppression(boxes, scores, thr)
+    area = (boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])
+    iou0 = ref_utils.compute_iou(boxes[0], boxes, area[0], area)
+    save("nms_utils", boxes=boxes, scores=scores, iou_row0=iou0, **out)
+
+
+def gen_refine():
+    rng = np.random.default_rng(13)
+    N, K = 120, 7
+    cfg = FusionConfig(NUM_CLASSES=K, DETECTION_MIN_CONFIDENCE=0.3, DETECTION_MAX_INSTANCES=20)
+    rois = syn.make_rois(rng, 1, N)[0]
+    probs, deltas = syn.make_detection_inputs(rng, N, K)
+    deltas *= 0.3
+    window = np.array([0.0, 0.02, 1.0, 0.97], np.float32)
+    det = quiet(mm.refine_detections_graph, T(rois), T(probs), T(deltas), T(window), cfg)
+    cfg0 = FusionConfig(NUM_CLASSES=K, DETECTION_MIN_CONFIDENCE=0, DETECTION_MAX_INSTANCES=20)
+    det0 = quiet(mm.refine_detections_graph, T(rois), T(probs), T(deltas), T(window), cfg0)
+    save("refine", rois=rois, probs=probs, deltas=deltas, window=window, det=arr(det), det_noconf=arr(det0))
+    # batched through DetectionLayer
+    B = 2
+    cfgb = FusionConfig(NUM_CLASSES=K, DETECTION_MIN_CONFIDENCE=0.3, DETECTION_MAX_INSTANCES=20, IMAGES_PER_GPU=B,
+                        IMAGE_SHAPE=np.array([96, 128, 3]))
+    rois_b = syn.make_rois(rng, B, N)
+    pd = [syn.make_detection_inputs(rng, N, K) for _ in range(B)]
+    probs_b = np.stack([p for p, _ in pd])
+    deltas_b = np.stack([d for _, d in pd]) * 0.3
+    meta = syn.make_image_meta(B, (96, 128, 3), K, window=(8, 0, 88, 128))
+    layer = mm.DetectionLayer(cfgb)
+    out = quiet(layer.call, [T(rois_b), T(probs_b), T(deltas_b), T(meta)])
+    save("detection_layer", rois=rois_b, probs=probs_b, deltas=deltas_b, image_meta=meta, out=arr(out))
+
+
+def gen_roi_align():
+    rng = np.random.default_rng(14)
+    B, R, C = 2, 40, 8
+    boxes = syn.make_rois(rng, B, R)
+    boxes[0, 0] = [0.0, 0.0, 1.0, 1.0]
+    boxes[0, 1] = [0.85, 0.9, 1.2, 1.3]
+    maps = [np.maximum(rng.standard_normal((B, s, s, C)), 0).astype(np.float32) for s in (32, 16, 8, 4)]
+    meta = syn.make_image_meta(B, (512, 512, 3), 3)
+    for pool in ((7, 7), (3, 5)):
+        layer = mm.PyramidROIAlign(pool)
+        out = quiet(layer.call, [T(boxes), T(meta)] + [T(m) for m in maps])
+        save("roi_align_%dx%d" % pool, boxes=boxes, image_meta=meta, P2=maps[0], P3=maps[1], P4=maps[2], P5=maps[3],
+             pool=np.asarray(pool), out=arr(out))
+
+
+def gen_proposals():
+    rng = np.random.default_rng(15)
+    B = 2
+    anchors = syn.make_anchors((64, 64), scales=(8, 16, 32), strides=(4, 8, 16))
+    A = anchors.shape[0]
+    cfg = FusionConfig(PRE_NMS_LIMIT=150, IMAGES_PER_GPU=B)
+    fg = (rng.permutation(B * A).reshape(B, A).astype(np.float32) + 1) / (B * A + 1)
+    probs = np.stack([1 - fg, fg], axis=-1).astype(np.float32)
+    bbox = rng.normal(0, 0.5, (B, A, 4)).astype(np.float32)
+    anc = np.broadcast_to(anchors, (B, A, 4)).copy()
+    layer = mm.ProposalLayer(proposal_count=40, nms_threshold=0.7, config=cfg)
+    out = quiet(layer.call, [T(probs), T(bbox), T(anc)])
+    save("proposals", probs=probs, bbox=bbox, anchors=anc, out=arr(out), pre_nms_limit=np.int32(150),
+         proposal_count=np.int32(40), nms_threshold=np.float32(0.7))
+
+
+def gen_convlstm():
+    rng = np.random.default_rng(16)
+    B, X, Y, Z, C = 1, 4, 3, 5, 4
+    F = C
+    cell = mm.ConvLSTMCell(shape=[X, Y, Z], kernel=[3, 3, 3], filters=F)
+    W = (rng.standard_normal((3, 3, 3, C + F, 4 * F)) * 0.15).astype(np.float32)
+    b = rng.normal(0, 0.1, 4 * F).astype(np.float32)
+    cell.W, cell.bias = T(W), T(b)
+    xs = rng.standard_normal((B, 3, X, Y, Z, C)).astype(np.float32)
+    c = np.zeros((B, X, Y, Z, F), np.float32)
+    h = np.zeros((B, X, Y, Z, F), np.float32)
+    hs, cs = [], []
+    for t in range(3):
+        out, (c, h) = quiet(cell.call, T(xs[:, t]), (T(c), T(h)))
+        hs.append(arr(h))
+        cs.append(arr(c))
+    save("convlstm", x=xs, W=W, b=b, h=np.stack(hs, 1), c=np.stack(cs, 1))
+
+
+def gen_poses():
+    """mrcnn/utils.py:1175-1218 quat2rot / vec2rot -- pure NumPy, run unmodified."""
+    rng = np.random.default_rng(17)
+    q = rng.normal(0, 1, (5, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)      # quat2rot is a rotation only for unit quaternions
+    vec = rng.normal(0, 2, (5, 9))
+    save("poses", quat=q, quat_R=np.stack([ref_utils.quat2rot(list(x)) for x in q]),
+         vec=vec, vec_R=np.stack([ref_utils.vec2rot(x) for x in vec]))
+
+
+if __name__ == "__main__":
+    gen_unproject_project()
+    gen_boxes()
+    gen_nms_utils()
+    gen_refine()
+    gen_roi_align()
+    gen_proposals()
+    gen_convlstm()
+    gen_poses()
