@@ -6,8 +6,7 @@
 //
 // Two kernels live here.  The production kernel is unproject_run_kernel (further down): a warp
 // owns a z-run of one voxel column and caches the bilinear 2x2 patch in registers.  The first
-// generation brick kernel below is kept for A/B measurement (MVF_K1_VARIANT=0) and for V > 1
-// shapes the run kernel does not cover.
+// generation brick kernel below is kept for A/B measurement only (MVF_K1_VARIANT=0).
 //
 // Brick kernel mapping: one CTA = one 4x4x16 brick of voxels of one scene; a warp owns 32 voxels of the
 // brick.  Lanes first work as 32 independent (voxel, view) coordinate units -- voxel->pixel
@@ -238,15 +237,24 @@ unproject_fuse_kernel(const __grid_constant__ UnprojParams p) {
 constexpr int RUN_WARPS = 8, RUN_TX = 4, RUN_TY = 2;
 
 // FULLC: C/4 is a multiple of 32*CPL, so no lane ever falls off the channel vector.
+//
+// What bounds this kernel is the register-return bandwidth of the load/store unit (128 B/clk/SM):
+// every byte a lane receives -- tap data, but also BROADCAST shared-memory reads -- crosses it.
+// So the per-step broadcast is kept to 8 bytes: ax = x1 - u and ay = y1 - w (two steps per
+// LDS.128); each lane forms bx = 1 - ax, by = 1 - ay and the four products itself (<= 1 ulp from
+// the reference's (u - x0), inside the 1e-5 feature tolerance; indices and validity masks stay
+// bit-exact, they come from phase A).  A reload reads one 32-bit word: the byte offset of the
+// cell's (y0,x0) tap with the complement of the 4 validity bits in its low nibble -- interior
+// cells (nibble 0) take the fast path with constant strides, border cells zero-fill per tap.
 template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC>
-__global__ void __launch_bounds__(RUN_WARPS * 32)
+__global__ void __launch_bounds__(RUN_WARPS * 32, (CPL * L <= 16) ? 2 : 1)
 unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
     constexpr int VPP = 32 / L;                       // views handled per phase A
-    static_assert(VPP * L == 32, "L must divide 32");
+    static_assert(VPP * L == 32 && (L % 2) == 0, "L must be even and divide 32");
     __shared__ float sKR[MVF_MAX_VIEWS][12];
     __shared__ float sOff[3];
-    __shared__ __align__(16) float4 sW[RUN_WARPS][32];   // the four bilinear weights (0 for an out-of-map tap)
-    __shared__ __align__(16) uint4 sO[RUN_WARPS][32];    // the four tap BYTE offsets inside a view (clamped into the map)
+    __shared__ __align__(16) float2 sA[RUN_WARPS][32];   // (ax, ay) per (view, z-step) slot
+    __shared__ __align__(16) uint4 sO[RUN_WARPS][32];    // four tap byte offsets (clamped into the map); .x low nibble = ~valid bits
 
     const int b = blockIdx.y / nchunk, chunk = blockIdx.y - b * nchunk;
     const int tid = threadIdx.x;
@@ -309,6 +317,7 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
 #pragma unroll
     for (int c = 0; c < CPL; ++c) lane_off[c] = 16u * (unsigned)(FULLC ? (c4base + 32 * c) : min(c4base + 32 * c, C4 - 1));
     const float* feats_b = p.feats + (size_t)b * V * view_stride;
+    const long long strideX = 4ll * C, strideY = 4ll * C * p.fw;      // bytes between x / y neighbours
 
     float gxv = p.gx[p.x_begin + ixs], gyv = p.gy[iy];
     if (world) { gxv = add_rn(gxv, sOff[0]); gyv = add_rn(gyv, sOff[1]); }
@@ -320,7 +329,6 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
     for (int k = 0; k < L; ++k)
 #pragma unroll
         for (int c = 0; c < CPL; ++c) acc[k][c] = zz;
-    // the patch stays finite (zero or real features), so a zero weight always contributes 0
     ulonglong2 tA[CPL], tB[CPL], tC[CPL], tD[CPL];
 #pragma unroll
     for (int c = 0; c < CPL; ++c) { tA[c] = zz; tB[c] = zz; tC[c] = zz; tD[c] = zz; }
@@ -331,8 +339,7 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
         {
             const int sub = lane / L, k = lane - sub * L;
             const int v = v0 + sub, iz = z0 + k;
-            float wa = 0.f, wb = 0.f, wc = 0.f, wd = 0.f;
-            uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
+            float ax = 0.f, ay = 0.f;
             int bits = 0, x0 = INT32_MIN, y0 = INT32_MIN;
             if (v < V && iz < p.Z) {
                 float z = p.gz[iz];
@@ -346,25 +353,11 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
                 if (usable_coord(u) && usable_coord(w)) {
                     const float x0f = floorf(u), y0f = floorf(w);            // :192-195
                     x0 = (int)x0f; y0 = (int)y0f;
-                    const float x1f = (float)(x0 + 1), y1f = (float)(y0 + 1);
-                    const float ax = sub_rn(x1f, u), bx = sub_rn(u, x0f);
-                    const float ay = sub_rn(y1f, w), by = sub_rn(w, y0f);
                     const bool inx0 = (x0 >= 0) && (x0 < p.fw), inx1 = (x0 + 1 >= 0) && (x0 + 1 < p.fw);
                     const bool iny0 = (y0 >= 0) && (y0 < p.fh), iny1 = (y0 + 1 >= 0) && (y0 + 1 < p.fh);
                     bits = (int)(iny0 && inx0) | ((int)(iny1 && inx0) << 1) | ((int)(iny0 && inx1) << 2) |
                            ((int)(iny1 && inx1) << 3);
-                    if (bits) {
-                        // weights of the reference (:214-217); an out-of-map tap reads 0 there (TF-GPU gather_nd),
-                        // here its weight is zeroed and its address clamped into the map instead
-                        wa = (bits & 1) ? mul_rn(ax, ay) : 0.f; wb = (bits & 2) ? mul_rn(ax, by) : 0.f;
-                        wc = (bits & 4) ? mul_rn(bx, ay) : 0.f; wd = (bits & 8) ? mul_rn(bx, by) : 0.f;
-                        const int xa = min(max(x0, 0), p.fw - 1), xb = min(max(x0 + 1, 0), p.fw - 1);
-                        const int ya = min(max(y0, 0), p.fh - 1), yb = min(max(y0 + 1, 0), p.fh - 1);
-                        const unsigned CB = 4u * (unsigned)C;
-                        const unsigned oa = (unsigned)(ya * p.fw + xa) * CB;
-                        const unsigned dX = (xb != xa) ? CB : 0u, dY = (yb != ya) ? (unsigned)p.fw * CB : 0u;
-                        o4 = make_uint4(oa, oa + dY, oa + dX, oa + dX + dY);
-                    }
+                    if (bits) { ax = sub_rn((float)(x0 + 1), u); ay = sub_rn((float)(y0 + 1), w); }   // :214-217
                 }
                 if (chunk == 0 && (p.out_idx || p.out_valid)) {
                     const size_t vox = (((size_t)b * V + v) * p.Xs + ixs) * p.Y * p.Z + (size_t)iy * p.Z + iz;
@@ -372,45 +365,74 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
                     if (p.out_valid) p.out_valid[vox] = (uint8_t)bits;
                 }
             }
-            // the patch is (re)loaded when this step samples a cell that differs from the previous
-            // step's (or follows a step that sampled nothing)
-            const int px0 = __shfl_up_sync(FULL, x0, 1), py0 = __shfl_up_sync(FULL, y0, 1);
-            const int pbits = __shfl_up_sync(FULL, bits, 1);
-            const bool reload = (bits != 0) && (k == 0 || pbits == 0 || px0 != x0 || py0 != y0);
+            // sampling state of this step: the cell, or "nothing" (-1).  The patch registers are
+            // refreshed whenever the state differs from the previous step's (always at a run start).
+            const int cell = bits ? (y0 * p.fw + x0) : INT32_MIN;
+            const int pcell = __shfl_up_sync(FULL, cell, 1), pbits = __shfl_up_sync(FULL, bits, 1);
+            const bool reload = (k == 0) || (cell != pcell) || (bits != pbits);   // bits: (y, fw-1) and (y+1, -1) share a cell id
             rmask = __ballot_sync(FULL, reload);
-            sW[warp][lane] = make_float4(wa, wb, wc, wd);
+            sA[warp][lane] = make_float2(ax, ay);
+            // tap byte offsets, each clamped into the map so that every load is legal; the complement of the
+            // validity bits rides in the low nibble of .x (offsets are multiples of 16): a tap that is outside
+            // the map is zeroed after the load (TF-GPU gather_nd zero fill)
+            uint4 o4 = make_uint4(15u, 0u, 0u, 0u);
+            if (bits) {
+                const int xa = min(max(x0, 0), p.fw - 1), xb = min(max(x0 + 1, 0), p.fw - 1);
+                const int ya = min(max(y0, 0), p.fh - 1), yb = min(max(y0 + 1, 0), p.fh - 1);
+                const unsigned CB = 4u * (unsigned)C;
+                const unsigned oa = (unsigned)(ya * p.fw + xa) * CB;
+                const unsigned dX = (xb != xa) ? CB : 0u, dY = (yb != ya) ? (unsigned)p.fw * CB : 0u;
+                o4 = make_uint4(oa | (unsigned)(15 ^ bits), oa + dY, oa + dX, oa + dX + dY);
+            }
             sO[warp][lane] = o4;
         }
         __syncwarp();
-        // ---- phase B: lanes = float4 channel slots
-#pragma unroll
+        // ---- phase B: lanes = float4 channel slots.  The view loop stays ROLLED (only the L z-steps are
+        // unrolled, they index the accumulator registers): the hot loop must fit the instruction cache.
+#pragma unroll 1
         for (int sub = 0; sub < VPP; ++sub) {
             const int vv = v0 + sub;
             if (vv >= V) break;
-            // per-lane 64-bit base of this view; a tap address is base + (warp-uniform 32-bit byte offset)
+            // per-lane 64-bit base of this view; a tap address is base + warp-uniform byte offset
             const char* vb[CPL];
 #pragma unroll
             for (int c = 0; c < CPL; ++c) vb[c] = (const char*)(feats_b + (size_t)vv * view_stride) + lane_off[FULLC ? 0 : c];
+            const unsigned vmask = rmask >> (sub * L);
+            const float2* aslot = &sA[warp][sub * L];
+            const uint4* oslot = &sO[warp][sub * L];
+            float4 aa = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < L; ++k) {
-                const int slot = sub * L + k;
-                if ((rmask >> slot) & 1u) {                                // warp-uniform
-                    const uint4 o = sO[warp][slot];                        // broadcast LDS.128
+                if ((vmask >> k) & 1u) {                                   // warp-uniform
+                    const uint4 o = oslot[k];                              // broadcast LDS.128
+                    const unsigned ox = o.x & ~15u;
 #pragma unroll
                     for (int c = 0; c < CPL; ++c) {
                         const char* q = FULLC ? vb[0] + 512 * c : vb[c];
-                        tA[c] = ldg2x2(q + o.x); tB[c] = ldg2x2(q + o.y); tC[c] = ldg2x2(q + o.z); tD[c] = ldg2x2(q + o.w);
+                        tA[c] = ldg2x2(q + ox); tB[c] = ldg2x2(q + o.y); tC[c] = ldg2x2(q + o.z); tD[c] = ldg2x2(q + o.w);
+                    }
+                    if (o.x & 15u) {                                       // rare: border cell / nothing sampled
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) {
+                            if (o.x & 1u) tA[c] = zz;
+                            if (o.x & 2u) tB[c] = zz;
+                            if (o.x & 4u) tC[c] = zz;
+                            if (o.x & 8u) tD[c] = zz;
+                        }
                     }
                 }
-                const float4 w = sW[warp][slot];                           // broadcast LDS.128
+                if ((k & 1) == 0) aa = *reinterpret_cast<const float4*>(aslot + k);   // broadcast LDS.128: two steps
+                const float ax = (k & 1) ? aa.z : aa.x, ay = (k & 1) ? aa.w : aa.y;
+                const float bx = 1.0f - ax, by = 1.0f - ay;
+                const float wa = ax * ay, wb = ax * by, wc = bx * ay, wd = bx * by;
                 if (MODE != MVF_FUSE_NONE && MODE != MVF_FUSE_MAX && !RELU_IN) {
 #pragma unroll
                     for (int c = 0; c < CPL; ++c)                          // 8 FFMA2 = 16 fp32 FMAs
-                        acc[k][c] = fma2x2(w.w, tD[c], fma2x2(w.z, tC[c], fma2x2(w.y, tB[c], fma2x2(w.x, tA[c], acc[k][c]))));
+                        acc[k][c] = fma2x2(wd, tD[c], fma2x2(wc, tC[c], fma2x2(wb, tB[c], fma2x2(wa, tA[c], acc[k][c]))));
                 } else {
 #pragma unroll
                     for (int c = 0; c < CPL; ++c) {
-                        float4 val = unpack4(fma2x2(w.w, tD[c], fma2x2(w.z, tC[c], fma2x2(w.y, tB[c], fma2x2(w.x, tA[c], zz)))));
+                        float4 val = unpack4(fma2x2(wd, tD[c], fma2x2(wc, tC[c], fma2x2(wb, tB[c], fma2x2(wa, tA[c], zz)))));
                         if (RELU_IN) val = relu4(val);
                         if (MODE == MVF_FUSE_NONE) {
                             if (z0 + k < p.Z && (FULLC || c4base + 32 * c < C4)) {
@@ -541,9 +563,11 @@ extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const f
     dim3 grid(tiles, B);
     cudaStream_t s = (cudaStream_t)stream;
     const int C4 = C / 4;
-    // MVF_K1_VARIANT (debug / A-B measurement): 0 = first-generation brick kernel, 1 = run kernel
-    // 128 ch x 16 z-steps per warp (default), 2 = run kernel 256 ch x 8 z-steps, 3 = 128 ch x 8 z-steps.
-    static const int variant = [] { const char* e = getenv("MVF_K1_VARIANT"); return e ? atoi(e) : 1; }();
+    // Default: the run kernel; one warp covers 256 channels x 8 z-steps when C is a multiple of 256 (the FPN
+    // width), else 128 channels x 16 z-steps.  MVF_K1_VARIANT (debug / A-B measurement) overrides:
+    // 0 = first-generation brick kernel, 1 = run 128ch x 16, 2 = run 256ch x 8, 3 = run 128ch x 8.
+    static const int variant = [] { const char* e = getenv("MVF_K1_VARIANT"); return e ? atoi(e) : -1; }();
+    if (variant < 0) return (C4 % 64 == 0) ? launch_run<2, 8>(p, B, s) : launch_run<1, 16>(p, B, s);
     if (variant == 1) return launch_run<1, 16>(p, B, s);
     if (variant == 2) return launch_run<2, 8>(p, B, s);
     if (variant == 3) return launch_run<1, 8>(p, B, s);
