@@ -288,6 +288,62 @@ def run_b200(args):
     return 0
 
 
+def run_cooperative(args):
+    """Strong-scaling measurement of the cooperative strategies: all ranks work on the
+    SAME --scenes scenes; the timed step includes the NCCL collective.  Extra to the headline line."""
+    import torch
+    import torch.distributed as dist
+    import mulit_view_object_detection_b200 as m
+    from mulit_view_object_detection_b200 import synthetic as syn, dist as mvd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.scenes
+    cfg = make_config(B)
+    feats, Rcam, Kmat = syn.make_scene(cfg, B, T["V"], T["fh"], T["fw"], T["C"], seed=1000)   # same scenes on every rank
+    d = [torch.from_numpy(a).to(dev) for a in (feats, Rcam, Kmat)]
+    fn = {"view_allreduce": mvd.view_shard_allreduce, "view_reduce_scatter": mvd.view_shard_reduce_scatter,
+          "slab_owner": mvd.slab_owner}[args.strategy]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        fn(*d, cfg, T["P"], mode="sum")
+    barrier()
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = m.launch_count()
+    e0.record(stream)
+    for _ in range(args.steps):
+        rays, _ = fn(*d, cfg, T["P"], mode="sum")
+    e1.record(stream)
+    barrier()
+    launches = m.launch_count() - n0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    if rank == 0:
+        value = B * T["V"] * T["nvox"] ** 3 * args.steps / (total_ms * 1e-3)
+        cfgd = workload_config(args, world)
+        cfgd["sharding"] = args.strategy
+        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                          "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
+                          "gpu_launches": int(launches), "checksum": float(rays.double().sum())}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,9 +352,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner"],
+                    help="multi-GPU sharding: scene (default, weak scaling, no collective) or one of the cooperative "
+                         "strategies of dist.py on a FIXED batch of --scenes scenes (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.strategy != "scene":
+        return run_cooperative(args)
     return run_b200(args)
 
 

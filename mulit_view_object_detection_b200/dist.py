@@ -1,0 +1,181 @@
+"""Multi-GPU sharding of the fusion path: one process per GPU, ``torch.distributed`` (NCCL over
+NVLink 5 / NVSwitch on the B200 box, gloo in the CPU tests) for the plumbing.
+
+The reference has no multi-GPU path at all (its ``GPU_COUNT > 1`` branch imports a module that
+does not exist, mrcnn/model_multi.py:2557-2559), so this layer is new; SURVEY.md section 8(e) is its spec.
+Four strategies, all producing the same ray slices ``proj_grid(grid_reas(unproj_feat(...)))``:
+
+* ``scene_shard``          scenes are independent: rank r takes scenes r::world, no collective.
+* ``view_shard_allreduce`` rank r unprojects its views into a full-size partial grid, one
+                           ``all_reduce(sum|max)`` over N*C*4 bytes, every rank projects.
+* ``view_shard_reduce_scatter``  partial grids are reduce-scattered into x-slabs, each rank
+                           projects from its slab only (a ray sample comes from exactly one
+                           slab, the others contribute 0) and the small ray tensor is all-reduced.
+* ``slab_owner``           features are tiny (13 MB for 8 views): every rank holds all views,
+                           unprojects ALL of them for its own x-slab (no grid exchange at all),
+                           projects locally, all-reduces the ray tensor.
+
+The compute steps go through an ``ops`` object (default: the CUDA layers of this package); the
+CPU tests inject an oracle-backed ``ops`` so that the sharding / collective logic is covered with
+``gloo`` at world_size 2 without a GPU.
+"""
+import torch
+import torch.distributed as dist
+
+
+class CudaOps:
+    """The product path: kernels of libmvfusion.so on torch CUDA tensors."""
+
+    def unproject_fuse(self, feats, Rcam, Kmat, config, mode, Rmain=None, x_slab=None):
+        from . import layers
+        return layers.unproject_fuse(feats, Rcam, Kmat, config, mode=mode, Rmain=Rmain, x_slab=x_slab)
+
+    def proj_grid(self, grid, Rcam, Kmat, config, proj_size, x_slab=None):
+        from . import layers
+        return layers.proj_grid([grid, Rcam, Kmat], config, proj_size, x_slab=x_slab)
+
+    def scale(self, grid, factor):
+        """grid * factor through the view-reduce kernel (V=1, per-channel scale)."""
+        from . import layers, _lib
+        C = grid.shape[-1]
+        scale = torch.full((C,), float(factor), dtype=torch.float32, device=grid.device)
+        shift = torch.zeros((C,), dtype=torch.float32, device=grid.device)
+        out = torch.empty_like(grid)
+        B = grid.shape[0]
+        rc = _lib.lib.mvf_view_reduce(layers._ptr(grid), B, 1, grid.numel() // (B * C), C, _lib.FUSE_SUM, 0,
+                                      layers._ptr(scale), layers._ptr(shift), layers._ptr(out), layers._stream())
+        _lib.check(rc, "mvf_view_reduce")
+        return out
+
+
+def world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def view_slice(V, rank, world_size):
+    """Contiguous, balanced split of the view axis: views [lo, hi) of rank ``rank``."""
+    base, rem = divmod(V, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def slab_bounds(X, rank, world_size):
+    """x-slab (x_begin, x_count) of rank ``rank``; X must divide evenly for reduce-scatter."""
+    base, rem = divmod(X, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, base + (1 if rank < rem else 0)
+
+
+def scene_indices(B, rank, world_size):
+    return list(range(rank, B, world_size))
+
+
+def _reduce_op(mode):
+    return dist.ReduceOp.MAX if mode == "max" else dist.ReduceOp.SUM
+
+
+def _all_reduce(t, op, group):
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=op, group=group)
+    return t
+
+
+def _reduce_scatter_x(partial, op, group):
+    """[B,X,Y,Z,C] partial grids -> this rank's reduced x-slab [B,X/W,Y,Z,C]."""
+    rank, ws = world(group)
+    if ws == 1:
+        return partial
+    B, X = partial.shape[:2]
+    if X % ws:
+        raise ValueError("reduce-scatter by slab needs nvox (%d) divisible by the world size (%d)" % (X, ws))
+    xs = X // ws
+    out = torch.empty((B, xs) + tuple(partial.shape[2:]), dtype=partial.dtype, device=partial.device)
+    if dist.get_backend(group) == "gloo":                # gloo has no reduce_scatter: reduce, then slice
+        full = partial.clone()
+        dist.all_reduce(full, op=op, group=group)
+        out.copy_(full[:, rank * xs:(rank + 1) * xs])
+        return out
+    for b in range(B):                                   # per scene the x-slabs are contiguous chunks
+        dist.reduce_scatter_tensor(out[b], partial[b].contiguous(), op=op, group=group)
+    return out
+
+
+def view_shard_allreduce(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None):
+    """``feats`` / ``Rcam`` hold ALL views on every rank (or at least this rank's slice is valid);
+    each rank unprojects views ``view_slice(V, rank, world)`` only.  Returns (rays, fused grid)."""
+    ops = ops or CudaOps()
+    rank, ws = world(group)
+    V = feats.shape[1]
+    lo, hi = view_slice(V, rank, ws)
+    Rmain = Rcam[:, 0].contiguous()
+    local_mode = "max" if mode == "max" else "sum"
+    if hi > lo:
+        partial = ops.unproject_fuse(feats[:, lo:hi].contiguous(), Rcam[:, lo:hi].contiguous(), Kmat, config,
+                                     local_mode, Rmain=Rmain)
+    else:                                                # more ranks than views: identity element
+        g = config
+        shape = (feats.shape[0], g.nvox, g.nvox, g.nvox_z, feats.shape[-1])
+        partial = torch.full(shape, float("-inf") if mode == "max" else 0.0, dtype=feats.dtype, device=feats.device)
+    fused = _all_reduce(partial, _reduce_op(mode), group)
+    if mode == "mean":
+        fused = ops.scale(fused, 1.0 / V)
+    rays = ops.proj_grid(fused, Rcam, Kmat, config, proj_size)
+    return rays, fused
+
+
+def view_shard_reduce_scatter(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None):
+    """View-sharded unprojection, reduce-scatter of the grid by x-slab, slab-local projection,
+    all-reduce(sum) of the ray slices.  Returns (rays, this rank's grid slab)."""
+    ops = ops or CudaOps()
+    rank, ws = world(group)
+    V = feats.shape[1]
+    lo, hi = view_slice(V, rank, ws)
+    if hi <= lo:
+        raise ValueError("view sharding needs at least one view per rank (V=%d, world=%d)" % (V, ws))
+    Rmain = Rcam[:, 0].contiguous()
+    partial = ops.unproject_fuse(feats[:, lo:hi].contiguous(), Rcam[:, lo:hi].contiguous(), Kmat, config,
+                                 "max" if mode == "max" else "sum", Rmain=Rmain)
+    slab = _reduce_scatter_x(partial, _reduce_op(mode), group)
+    if mode == "mean":
+        slab = ops.scale(slab, 1.0 / V)
+    xb, xc = slab_bounds(config.nvox, rank, ws)
+    rays = ops.proj_grid(slab, Rcam, Kmat, config, proj_size, x_slab=(xb, xc))
+    rays = _all_reduce(rays, dist.ReduceOp.SUM, group)
+    return rays, slab
+
+
+def slab_owner(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None):
+    """Owner-computes: every rank holds all views and fuses ALL of them for its own x-slab;
+    the only exchange is the all-reduce(sum) of the ray slices.  Returns (rays, grid slab)."""
+    ops = ops or CudaOps()
+    rank, ws = world(group)
+    xb, xc = slab_bounds(config.nvox, rank, ws)
+    slab = ops.unproject_fuse(feats, Rcam, Kmat, config, mode, x_slab=(xb, xc))
+    rays = ops.proj_grid(slab, Rcam, Kmat, config, proj_size, x_slab=(xb, xc))
+    rays = _all_reduce(rays, dist.ReduceOp.SUM, group)
+    return rays, slab
+
+
+def scene_shard(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None, gather=False):
+    """Data parallel over scenes: rank r processes scenes r::world with no collective.
+    With ``gather`` the per-rank ray slices are all-gathered back into scene order."""
+    ops = ops or CudaOps()
+    rank, ws = world(group)
+    B = feats.shape[0]
+    mine = scene_indices(B, rank, ws)
+    idx = torch.as_tensor(mine, dtype=torch.long, device=feats.device)
+    f, R, K = feats.index_select(0, idx), Rcam.index_select(0, idx), Kmat.index_select(0, idx)
+    fused = ops.unproject_fuse(f, R, K, config, mode)
+    rays = ops.proj_grid(fused, R, K, config, proj_size)
+    if not gather or ws == 1:
+        return rays, mine
+    if B % ws:
+        raise ValueError("gather needs the scene count (%d) divisible by the world size (%d)" % (B, ws))
+    parts = [torch.empty_like(rays) for _ in range(ws)]
+    dist.all_gather(parts, rays, group=group)
+    out = torch.empty((B,) + tuple(rays.shape[1:]), dtype=rays.dtype, device=rays.device)
+    for r in range(ws):
+        out[r::ws] = parts[r]
+    return out, mine

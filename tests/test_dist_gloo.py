@@ -1,0 +1,102 @@
+"""CPU: the multi-GPU sharding logic (mulit_view_object_detection_b200/dist.py) at world_size 2 over
+gloo.  The compute steps are injected from the oracle (no GPU here); what is under test is the
+view / slab / scene partitioning, the Rmain plumbing and the collectives."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from helpers import small_cfg, scene
+
+
+class OracleOps:
+    """dist.py's ``ops`` interface on torch CPU tensors, backed by the NumPy oracle."""
+
+    def unproject_fuse(self, feats, Rcam, Kmat, config, mode, Rmain=None, x_slab=None):
+        f, R, K = feats.numpy(), Rcam.numpy(), Kmat.numpy()
+        if Rmain is not None:                       # oracle takes the main pose as view 0: prepend it with zero features
+            R = np.concatenate([Rmain.numpy()[:, None], R], axis=1)
+            f = np.concatenate([np.zeros_like(f[:, :1]), f], axis=1)
+            per_view = oracle.unproj_feat(f, R, K, config)[:, 1:]
+        else:
+            per_view = oracle.unproj_feat(f, R, K, config)
+        fused = oracle.fuse_views(per_view, mode)
+        if x_slab is not None:
+            fused = fused[:, x_slab[0]:x_slab[0] + x_slab[1]]
+        return torch.from_numpy(np.ascontiguousarray(fused))
+
+    def proj_grid(self, grid, Rcam, Kmat, config, proj_size, x_slab=None):
+        g = grid.numpy()
+        if x_slab is not None:                      # a slab only answers for its own x range
+            full = np.zeros((g.shape[0], config.nvox) + g.shape[2:], np.float32)
+            full[:, x_slab[0]:x_slab[0] + x_slab[1]] = g
+            g = full
+        return torch.from_numpy(oracle.proj_grid(g, Rcam.numpy(), Kmat.numpy(), config, proj_size))
+
+    def scale(self, grid, factor):
+        return grid * np.float32(factor)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world_size, port, strategy, mode, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from mulit_view_object_detection_b200 import dist as mvd
+        cfg = small_cfg(nvox=8, nvox_z=6, samples=4, NUM_VIEWS=3)
+        feats, Rcam, Kmat = scene(cfg, 2, 3, 12, 12, 8, seed=5)
+        t = [torch.from_numpy(a) for a in (feats, Rcam, Kmat)]
+        ops = OracleOps()
+        if strategy == "scene":
+            rays, mine = mvd.scene_shard(*t, cfg, 10, mode=mode, ops=ops, gather=True)
+        else:
+            fn = {"allreduce": mvd.view_shard_allreduce, "reduce_scatter": mvd.view_shard_reduce_scatter,
+                  "slab_owner": mvd.slab_owner}[strategy]
+            rays, _ = fn(*t, cfg, 10, mode=mode, ops=ops)
+        np.save(os.path.join(out_dir, "rays_%d.npy" % rank), rays.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("strategy,mode", [("allreduce", "sum"), ("allreduce", "max"), ("allreduce", "mean"),
+                                           ("reduce_scatter", "sum"), ("reduce_scatter", "max"),
+                                           ("slab_owner", "sum"), ("slab_owner", "max"), ("scene", "sum")])
+def test_two_rank_strategies_match_single_process(strategy, mode, tmp_path):
+    world_size = 2
+    mp.spawn(_worker, args=(world_size, _free_port(), strategy, mode, str(tmp_path)), nprocs=world_size, join=True)
+    cfg = small_cfg(nvox=8, nvox_z=6, samples=4, NUM_VIEWS=3)
+    feats, Rcam, Kmat = scene(cfg, 2, 3, 12, 12, 8, seed=5)
+    ref = oracle.proj_grid(oracle.fuse_views(oracle.unproj_feat(feats, Rcam, Kmat, cfg), mode), Rcam, Kmat, cfg, 10)
+    for r in range(world_size):
+        got = np.load(os.path.join(str(tmp_path), "rays_%d.npy" % r))
+        # sum order differs between shardings (per-rank partial sums): 1e-5 relative; max is exact
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+        if mode == "max":
+            assert np.array_equal(got, ref)
+
+
+def test_partition_helpers():
+    from mulit_view_object_detection_b200 import dist as mvd
+    for V, W in ((8, 2), (8, 8), (5, 4), (3, 8)):
+        cover = []
+        for r in range(W):
+            lo, hi = mvd.view_slice(V, r, W)
+            cover += list(range(lo, hi))
+        assert cover == list(range(V))
+    for X, W in ((64, 8), (48, 4), (10, 4)):
+        spans = [mvd.slab_bounds(X, r, W) for r in range(W)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == X
+        assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+    assert mvd.scene_indices(7, 1, 3) == [1, 4]

@@ -1,0 +1,59 @@
+"""GPU (needs >= 2 devices): the cooperative strategies of dist.py over NCCL vs the single-GPU
+pipeline.  Skipped on a 1-GPU box; the gloo twin in test_dist_gloo.py always runs on CPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world_size, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=torch.device("cuda", rank))
+    try:
+        import mulit_view_object_detection_b200 as m
+        from mulit_view_object_detection_b200 import dist as mvd
+        from helpers import small_cfg, scene
+        cfg = small_cfg(nvox=16, nvox_z=16, samples=6, NUM_VIEWS=4)
+        feats, Rcam, Kmat = scene(cfg, 2, 4, 40, 40, 64, seed=21)
+        d = [torch.from_numpy(a).cuda() for a in (feats, Rcam, Kmat)]
+        ref, _ = m.unproject_fuse_project(*d, cfg, 24, mode="sum")
+        res = {}
+        for name, fn in (("allreduce", mvd.view_shard_allreduce), ("reduce_scatter", mvd.view_shard_reduce_scatter),
+                         ("slab_owner", mvd.slab_owner)):
+            rays, _ = fn(*d, cfg, 24, mode="sum")
+            res[name] = float((rays - ref).abs().max() / ref.abs().max())
+        rays, _ = mvd.scene_shard(*d, cfg, 24, mode="sum", gather=True)
+        res["scene"] = float((rays - ref).abs().max())
+        refm, _ = m.unproject_fuse_project(*d, cfg, 24, mode="max")
+        raysm, _ = mvd.view_shard_reduce_scatter(*d, cfg, 24, mode="max")
+        res["max_exact"] = float((raysm - refm).abs().max())
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, "res_%d.npy" % rank), np.array([res[k] for k in sorted(res)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_strategies_match_single_gpu(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        allreduce, max_exact, reduce_scatter, scene_err, slab_owner = np.load(os.path.join(str(tmp_path), "res_%d.npy" % r))
+        assert allreduce < 1e-5 and reduce_scatter < 1e-5 and slab_owner < 1e-5      # partial-sum order differs
+        assert scene_err == 0.0 and max_exact == 0.0
