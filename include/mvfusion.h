@@ -14,7 +14,8 @@
  *    addresses 16-byte aligned (128-bit vector access); violations return MVF_EALIGN.
  *  - The caller owns every buffer (inputs, outputs, workspaces).  The library never
  *    allocates or frees device memory, never synchronises the stream (except the *_host
- *    entry point, documented there) and keeps no state besides a launch counter.
+ *    entry point, documented there) and keeps no state besides a launch counter and the two
+ *    lazily created copy streams of the *_host entry point.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *  - Return value: MVF_OK (0) or a negative MVF_E* code; mvf_error_string() describes it.
  *  - Thread-safe and re-entrant per stream.
@@ -188,8 +189,9 @@ int mvf_proposals(const float* rpn_probs, const float* rpn_bbox, const float* an
 /* ---- fused pipeline through HOST buffers (the end-to-end entry) -----------------------------
  * unproj_feat -> grid_reas(sum|mean|max [+BN+ReLU]) -> proj_grid for B scenes whose inputs and
  * outputs live in (preferably pinned) HOST memory: copies feats/Rcam/Kmat host->device, runs
- * K1 + K3 on `stream`, copies the ray slices [B,S,ph,pw,C] back and SYNCHRONISES the stream
- * before returning.  dev_ws: mvf_pipeline_host_workspace_bytes(...) bytes of device scratch. */
+ * K1 + K3 and copies the ray slices [B,S,ph,pw,C] back, software-pipelined per scene over two
+ * internal streams (ordered after `stream`) so H2D, kernels and D2H overlap, and SYNCHRONISES
+ * `stream` before returning.  dev_ws: mvf_pipeline_host_workspace_bytes(...) bytes of device scratch. */
 size_t mvf_pipeline_host_workspace_bytes(const MvfGrid* g, int B, int V, int fh, int fw, int C,
                                          int proj_h, int proj_w, int samples);
 int mvf_unproject_fuse_project_host(const float* h_feats, const float* h_Rcam, const float* h_Kmat,

@@ -1,5 +1,6 @@
 // Library-level entry points: error strings, launch counter and the HOST-buffer pipeline.
 #include "mvf_common.cuh"
+#include <mutex>
 
 namespace mvf {
 std::atomic<unsigned long long> g_launches{0};
@@ -48,8 +49,35 @@ extern "C" size_t mvf_pipeline_host_workspace_bytes(const MvfGrid* g, int B, int
     return carve_host(nullptr, g, B, V, fh, fw, C, proj_h, proj_w, samples).bytes;
 }
 
+// Auxiliary streams/events of the host entry point, created lazily once per device (the only
+// library state besides the launch counter): copy-in + kernels run on `sc`, copy-out on `sd`, so
+// the H2D of scene-chunk i+1, the kernels of chunk i and the D2H of chunk i-1 overlap.
+namespace {
+constexpr int kMaxChunks = 32;
+struct Aux { bool ok = false; cudaStream_t sc = nullptr, sd = nullptr; cudaEvent_t start = nullptr, done_c = nullptr, done_d = nullptr; cudaEvent_t ev[kMaxChunks] = {}; };
+Aux g_aux[64];
+std::mutex g_aux_mu;
+Aux* get_aux() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_aux_mu);
+    Aux& a = g_aux[dev];
+    if (!a.ok) {
+        if (cudaStreamCreateWithFlags(&a.sc, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaStreamCreateWithFlags(&a.sd, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&a.start, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&a.done_c, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&a.done_d, cudaEventDisableTiming);
+        for (int i = 0; i < kMaxChunks; ++i) cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming);
+        a.ok = true;
+    }
+    return &a;
+}
+}  // namespace
+
 // The reference crosses host->device once per predict() call (mrcnn/model_multi.py:3067-3068);
-// this is the same crossing for the fusion path alone: H2D inputs, K1, K3, D2H ray slices.
+// this is the same crossing for the fusion path alone: H2D inputs, K1, K3, D2H ray slices,
+// software-pipelined over chunks of scenes.
 extern "C" int mvf_unproject_fuse_project_host(const float* h_feats, const float* h_Rcam, const float* h_Kmat,
                                                const MvfGrid* g, int B, int V, int fh, int fw, int C,
                                                int img_h, int img_w, int mode, int flags,
@@ -62,23 +90,45 @@ extern "C" int mvf_unproject_fuse_project_host(const float* h_feats, const float
     if (!aligned16(dev_ws)) return MVF_EALIGN;
     HostWs w = carve_host(dev_ws, g, B, V, fh, fw, C, proj_h, proj_w, samples);
     if (dev_ws_bytes < w.bytes) return MVF_EWORKSPACE;
+    Aux* ax = get_aux();
+    if (!ax) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t feat_bytes = (size_t)B * V * fh * fw * C * sizeof(float);
-    const size_t out_bytes = (size_t)B * samples * proj_h * proj_w * C * sizeof(float);
-    if (cudaMemcpyAsync(w.feats, h_feats, feat_bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) return MVF_ECUDA;
-    if (cudaMemcpyAsync(w.Rcam, h_Rcam, (size_t)B * V * 12 * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess) return MVF_ECUDA;
-    if (cudaMemcpyAsync(w.Kmat, h_Kmat, (size_t)B * 9 * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess) return MVF_ECUDA;
-    int rc = mvf_unproject_fuse(w.feats, w.Rcam, nullptr, w.Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, 0.0, 0, 0,
-                                d_bn_scale, d_bn_shift, w.grid, nullptr, nullptr, nullptr, stream);
-    if (rc != MVF_OK) return rc;
-    // proj_grid reads the main-view poses as a contiguous [B,3,4] tensor (Rcam[:,0], model_multi.py:245):
-    // compact them out of [B,V,3,4] with one strided device copy.
-    if (cudaMemcpy2DAsync(w.R0, 12 * sizeof(float), w.Rcam, (size_t)V * 12 * sizeof(float), 12 * sizeof(float), B,
-                          cudaMemcpyDeviceToDevice, s) != cudaSuccess) return MVF_ECUDA;
-    rc = mvf_project_rays(w.grid, w.R0, nullptr, w.Kmat, nullptr, g, B, C, img_h, proj_h, proj_w, samples,
-                          flags & ~MVF_FLAG_WORLD_GRID, 0.0, 0, 0, w.out, nullptr, nullptr, stream);
-    if (rc != MVF_OK) return rc;
-    if (cudaMemcpyAsync(h_out, w.out, out_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) return MVF_ECUDA;
-    if (cudaStreamSynchronize(s) != cudaSuccess) return MVF_ECUDA;
+    const size_t feat_scene = (size_t)V * fh * fw * C;
+    const size_t grid_scene = (size_t)g->nvox * g->nvox * g->nvox_z * C;
+    const size_t out_scene = (size_t)samples * proj_h * proj_w * C;
+#define MVF_TRY(x) do { if ((x) != cudaSuccess) return MVF_ECUDA; } while (0)
+    // order the auxiliary streams after whatever the caller queued on `stream`
+    MVF_TRY(cudaEventRecord(ax->start, s));
+    MVF_TRY(cudaStreamWaitEvent(ax->sc, ax->start, 0));
+    MVF_TRY(cudaStreamWaitEvent(ax->sd, ax->start, 0));
+    MVF_TRY(cudaMemcpyAsync(w.Rcam, h_Rcam, (size_t)B * V * 12 * sizeof(float), cudaMemcpyHostToDevice, ax->sc));
+    MVF_TRY(cudaMemcpyAsync(w.Kmat, h_Kmat, (size_t)B * 9 * sizeof(float), cudaMemcpyHostToDevice, ax->sc));
+    // proj_grid reads the main-view poses as a contiguous [B,3,4] tensor (Rcam[:,0], model_multi.py:245)
+    MVF_TRY(cudaMemcpy2DAsync(w.R0, 12 * sizeof(float), w.Rcam, (size_t)V * 12 * sizeof(float), 12 * sizeof(float), B,
+                              cudaMemcpyDeviceToDevice, ax->sc));
+    const int per = (B + kMaxChunks - 1) / kMaxChunks;          // scenes per chunk (1 unless B > 32)
+    int chunk = 0;
+    for (int b0 = 0; b0 < B; b0 += per, ++chunk) {
+        const int nb = (b0 + per <= B) ? per : (B - b0);
+        MVF_TRY(cudaMemcpyAsync(w.feats + b0 * feat_scene, h_feats + b0 * feat_scene, nb * feat_scene * sizeof(float),
+                                cudaMemcpyHostToDevice, ax->sc));
+        int rc = mvf_unproject_fuse(w.feats + b0 * feat_scene, w.Rcam + (size_t)b0 * V * 12, nullptr, w.Kmat + (size_t)b0 * 9, g,
+                                    nb, V, fh, fw, C, img_h, img_w, mode, flags & ~MVF_FLAG_WORLD_GRID, 0.0, 0, 0,
+                                    d_bn_scale, d_bn_shift, w.grid + b0 * grid_scene, nullptr, nullptr, nullptr, ax->sc);
+        if (rc != MVF_OK) return rc;
+        rc = mvf_project_rays(w.grid + b0 * grid_scene, w.R0 + (size_t)b0 * 12, nullptr, w.Kmat + (size_t)b0 * 9, nullptr, g,
+                              nb, C, img_h, proj_h, proj_w, samples, 0, 0.0, 0, 0, w.out + b0 * out_scene, nullptr, nullptr, ax->sc);
+        if (rc != MVF_OK) return rc;
+        MVF_TRY(cudaEventRecord(ax->ev[chunk], ax->sc));
+        MVF_TRY(cudaStreamWaitEvent(ax->sd, ax->ev[chunk], 0));
+        MVF_TRY(cudaMemcpyAsync(h_out + b0 * out_scene, w.out + b0 * out_scene, nb * out_scene * sizeof(float),
+                                cudaMemcpyDeviceToHost, ax->sd));
+    }
+    MVF_TRY(cudaEventRecord(ax->done_c, ax->sc));
+    MVF_TRY(cudaEventRecord(ax->done_d, ax->sd));
+    MVF_TRY(cudaStreamWaitEvent(s, ax->done_c, 0));
+    MVF_TRY(cudaStreamWaitEvent(s, ax->done_d, 0));
+    MVF_TRY(cudaStreamSynchronize(s));
+#undef MVF_TRY
     return MVF_OK;
 }

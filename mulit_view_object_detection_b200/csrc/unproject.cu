@@ -4,27 +4,11 @@
 // world-frame notebook variant Notebook/projection.py:47-151.  The per-view grids
 // [B,V,X,Y,Z,C] are never materialised unless mode == MVF_FUSE_NONE.
 //
-// Two kernels live here.  The production kernel is unproject_run_kernel (further down): a warp
-// owns a z-run of one voxel column and caches the bilinear 2x2 patch in registers.  The first
-// generation brick kernel below is kept for A/B measurement only (MVF_K1_VARIANT=0).
-//
-// Brick kernel mapping: one CTA = one 4x4x16 brick of voxels of one scene; a warp owns 32 voxels of the
-// brick.  Lanes first work as 32 independent (voxel, view) coordinate units -- voxel->pixel
-// projection, floor, the four weights and the tap-validity bits are computed ONCE per pair in
-// registers with individually rounded fp32 ops (bit-exact against the oracle) -- and then the
-// warp walks the 32 pairs: every pair's parameters are broadcast with shuffles and the 32 lanes
-// become 32 float4 channel slots, so every tap is one coalesced 128-bit read-only load per lane
-// (512 B per warp instruction) and every voxel one coalesced streaming 128-bit store.
-// The view reduction lives in the accumulator registers.
+// One kernel lives here: unproject_slot_kernel (design notes above its definition).
 #include "mvf_common.cuh"
 #include <stdlib.h>
 
 namespace mvf {
-
-constexpr int BRICK_X = 4, BRICK_Y = 4, BRICK_Z = 16;
-constexpr int K1_THREADS = 256;
-constexpr int K1_WARPS = K1_THREADS / 32;
-static_assert(BRICK_X * BRICK_Y * BRICK_Z == K1_WARPS * 32, "one voxel per (warp, lane)");
 
 struct UnprojParams {
     const float* feats; const float* Rcam; const float* Rmain; const float* Kmat;
@@ -36,16 +20,47 @@ struct UnprojParams {
     float gx[MVF_MAX_DIM], gy[MVF_MAX_DIM], gz[MVF_MAX_DIM];
 };
 
-template <int CPL, int MODE>
-__global__ void __launch_bounds__(K1_THREADS)
-unproject_fuse_kernel(const __grid_constant__ UnprojParams p) {
+
+// ---------------------------------------------------------------------------------------------
+// Slot kernel (production).  A warp owns L consecutive z-voxels of ONE (ix,iy) column for ONE
+// chunk of 128*CPL channels; a CTA (8 warps = 4x2 columns) walks a range of z-tiles so that the
+// pose prologue is paid once per many voxels.  All L accumulators stay in registers across the
+// whole view loop (the per-view grids never exist).
+//
+// What bounds this op on B200 is neither HBM nor FMA but the register-return path of the
+// load/store unit: measured (tools/microbench*.cu, profiles/microbench_r1.txt) a coalesced
+// LDG.128 costs 4.0 SM-cycles wherever it hits, a broadcast LDS.128 2.4, while the 16 FFMA2 of
+// one (voxel, view) step cost 8.2.  A naive gather needs 4 taps x 1 KB = 32 LSU cycles per step.
+// So the kernel is organised around loading as few tap vectors as possible:
+//   * the bilinear 2x2 patch lives in four register SLOTS addressed by coordinate PARITY:
+//     slot (r,c) holds the tap whose row has parity r and whose column has parity c.  When the
+//     projected pixel crosses into the next cell along the z-run only the slots whose
+//     coordinate changed are reloaded (2 of 4 for an axis-aligned move) and nothing is shuffled
+//     between registers; the weights are assigned per slot instead (0.95 tap loads per
+//     (voxel, view) on workload T instead of 4);
+//   * steps whose four taps are all outside the map (21 % on T) skip loads and FMAs altogether;
+//   * the per-step broadcast is 8 bytes: the weights of slot column 0 / slot row 0; the lane
+//     forms the complements (exact for coordinates >= 1, Sterbenz) and the four products itself.
+//   phase A (lanes = (view, z-step) pairs): voxel->pixel projection, floor, weights, validity and
+//           the per-slot "reload" flags, individually rounded fp32 (bit-exact vs the oracle),
+//           written to a 32-slot per-warp shared-memory table; masks travel as ballots;
+//   phase B (lanes = float4 channel slots): walk the run.
+constexpr int RUN_WARPS = 8, RUN_TX = 4, RUN_TY = 2;
+
+template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC>
+__global__ void __launch_bounds__(RUN_WARPS * 32, (CPL * L <= 16) ? 2 : 1)
+unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zsplit) {
+    constexpr int VPP = 32 / L;                       // views handled per phase A
+    constexpr bool PLAIN = (MODE == MVF_FUSE_SUM || MODE == MVF_FUSE_MEAN) && !RELU_IN;   // accumulate straight into acc
+    static_assert(VPP * L == 32 && (L % 2) == 0, "L must be even and divide 32");
     __shared__ float sKR[MVF_MAX_VIEWS][12];
     __shared__ float sOff[3];
+    __shared__ __align__(16) float2 sW[RUN_WARPS][32];   // (weight of slot column 0, weight of slot row 0) per (view, z-step)
+    __shared__ __align__(16) uint4 sO[RUN_WARPS][32];    // byte offsets of slots 00,01,10,11 (clamped into the map); .x low nibble = out-of-map bits
 
-    const int b = blockIdx.y;
+    const int b = blockIdx.y / nchunk, chunk = blockIdx.y - b * nchunk;
     const int tid = threadIdx.x;
     const bool world = (p.flags & MVF_FLAG_WORLD_GRID) != 0;
-
     // ---- prologue: KR_v = (K . [R_v^T | -R_v^T t_v]) . [[R_0|t_0],[0 0 0 1]]   (:137-147, :175-180)
     if (tid < p.V) {
         const float* P = p.Rcam + ((size_t)b * p.V + tid) * 12;
@@ -78,217 +93,6 @@ unproject_fuse_kernel(const __grid_constant__ UnprojParams p) {
         const float* P0 = p.Rmain ? p.Rmain + (size_t)b * 12 : p.Rcam + (size_t)b * p.V * 12;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const float v = dot4_rn(P0[i * 4 + 0], P0[i * 4 + 1], P0[i * 4 + 2], P0[i * 4 + 3],
-                                    0.0f, 0.0f, p.grid_dist, 1.0f);
-            sOff[i] = v;
-            if (p.out_grid_pos && blockIdx.x == 0) p.out_grid_pos[b * 3 + i] = v;
-        }
-    }
-    __syncthreads();
-
-    // ---- brick / voxel assignment
-    const int tiles_z = (p.Z + BRICK_Z - 1) / BRICK_Z;
-    const int tiles_y = (p.Y + BRICK_Y - 1) / BRICK_Y;
-    int t = blockIdx.x;
-    const int tz = t % tiles_z; t /= tiles_z;
-    const int ty = t % tiles_y; t /= tiles_y;
-    const int tx = t;
-    const int warp = tid >> 5, lane = tid & 31;
-    const unsigned FULL = 0xffffffffu;
-
-    const int C = p.C, V = p.V;
-    const int C4 = C >> 2;
-    const size_t view_stride = (size_t)p.fh * p.fw * C;
-    const float* feats_b = p.feats + (size_t)b * V * view_stride;
-    const int row_stride = p.fw * C;
-
-    float4 acc[CPL];
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) acc[k] = zero4();
-
-    const int npairs = 32 * V;
-    for (int q0 = 0; q0 < npairs; q0 += 32) {
-        // ---- phase 1: lane = one (voxel, view) pair
-        const int q = q0 + lane;
-        const int lv = q / V;                    // voxel slot 0..31 of this warp
-        const int v = q - lv * V;
-        const int l = warp * 32 + lv;            // voxel index inside the brick (z fastest)
-        const int iz = tz * BRICK_Z + (l % BRICK_Z);
-        const int iy = ty * BRICK_Y + ((l / BRICK_Z) % BRICK_Y);
-        const int ixs = tx * BRICK_X + (l / (BRICK_Z * BRICK_Y));      // index inside the slab
-        const bool in_grid = (iz < p.Z) && (iy < p.Y) && (ixs < p.Xs);
-        int my_bits = 0, my_off = 0;
-        float wa = 0.f, wb = 0.f, wc = 0.f, wd = 0.f;
-        if (in_grid) {
-            float x = p.gx[p.x_begin + ixs], y = p.gy[iy], z = p.gz[iz];
-            if (world) { x = add_rn(x, sOff[0]); y = add_rn(y, sOff[1]); z = add_rn(z, sOff[2]); }
-            const float* KR = sKR[v];
-            const float px = affine_row(KR, 0, x, y, z);
-            const float py = affine_row(KR, 1, x, y, z);
-            const float pz = affine_row(KR, 2, x, y, z);
-            const float u = mul_rn(div_rn(px, pz), p.sx);               // :187
-            const float w = mul_rn(div_rn(py, pz), p.sy);               // :188
-            int x0 = INT32_MIN, y0 = INT32_MIN;
-            if (usable_coord(u) && usable_coord(w)) {
-                const float x0f = floorf(u), y0f = floorf(w);            // :192-195
-                x0 = (int)x0f; y0 = (int)y0f;
-                const float x1f = (float)(x0 + 1), y1f = (float)(y0 + 1);
-                const float ax = sub_rn(x1f, u), bx = sub_rn(u, x0f);
-                const float ay = sub_rn(y1f, w), by = sub_rn(w, y0f);
-                wa = mul_rn(ax, ay); wb = mul_rn(ax, by); wc = mul_rn(bx, ay); wd = mul_rn(bx, by);   // :214-217
-                const bool inx0 = (x0 >= 0) && (x0 < p.fw), inx1 = (x0 + 1 >= 0) && (x0 + 1 < p.fw);
-                const bool iny0 = (y0 >= 0) && (y0 < p.fh), iny1 = (y0 + 1 >= 0) && (y0 + 1 < p.fh);
-                my_bits = (int)(iny0 && inx0) | ((int)(iny1 && inx0) << 1) | ((int)(iny0 && inx1) << 2) |
-                          ((int)(iny1 && inx1) << 3);
-                if (my_bits) my_off = (y0 * p.fw + x0) * C;              // may be negative: only valid taps are read
-            }
-            const size_t vox = (((size_t)b * V + v) * p.Xs + ixs) * p.Y * p.Z + (size_t)iy * p.Z + iz;
-            if (p.out_idx) { p.out_idx[vox * 2 + 0] = y0; p.out_idx[vox * 2 + 1] = x0; }
-            if (p.out_valid) p.out_valid[vox] = (uint8_t)my_bits;
-            my_bits |= 16;                                               // bit4: voxel is inside the grid
-        }
-
-        // ---- phase 2: lanes = float4 channel slots; walk the 32 pairs of this chunk
-        const int jmax = min(32, npairs - q0);
-        for (int j = 0; j < jmax; ++j) {
-            const int bits = __shfl_sync(FULL, my_bits, j);
-            const int qq = q0 + j;
-            const int jlv = qq / V;
-            const int jv = qq - jlv * V;
-            if (!(bits & 16)) continue;                                  // warp-uniform
-            float4 val[CPL];
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) val[k] = zero4();
-            if (bits & 15) {
-                const int off = __shfl_sync(FULL, my_off, j);
-                const float fa = __shfl_sync(FULL, wa, j), fb = __shfl_sync(FULL, wb, j);
-                const float fc = __shfl_sync(FULL, wc, j), fd = __shfl_sync(FULL, wd, j);
-                const float* base = feats_b + (size_t)jv * view_stride + off;
-#pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    const int c4 = lane + 32 * k;
-                    if (c4 < C4) {
-                        const float* pc = base + 4 * c4;
-                        if (bits & 1) val[k] = fma4(fa, ldg4(pc), val[k]);
-                        if (bits & 2) val[k] = fma4(fb, ldg4(pc + row_stride), val[k]);
-                        if (bits & 4) val[k] = fma4(fc, ldg4(pc + C), val[k]);
-                        if (bits & 8) val[k] = fma4(fd, ldg4(pc + row_stride + C), val[k]);
-                    }
-                }
-            }
-            if (p.flags & MVF_FLAG_RELU_IN) {
-#pragma unroll
-                for (int k = 0; k < CPL; ++k) val[k] = relu4(val[k]);
-            }
-            // voxel coordinates of pair j (warp-uniform)
-            const int jl = warp * 32 + jlv;
-            const int jz = tz * BRICK_Z + (jl % BRICK_Z);
-            const int jy = ty * BRICK_Y + ((jl / BRICK_Z) % BRICK_Y);
-            const int jx = tx * BRICK_X + (jl / (BRICK_Z * BRICK_Y));
-            if (MODE == MVF_FUSE_NONE) {
-                float* o = p.out + ((((size_t)b * V + jv) * p.Xs + jx) * p.Y * p.Z + (size_t)jy * p.Z + jz) * C;
-#pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    const int c4 = lane + 32 * k;
-                    if (c4 < C4) stcs4(o + 4 * c4, val[k]);
-                }
-                continue;
-            }
-#pragma unroll
-            for (int k = 0; k < CPL; ++k) {
-                if (MODE == MVF_FUSE_MAX) acc[k] = (jv == 0) ? val[k] : max4(acc[k], val[k]);
-                else acc[k] = (jv == 0) ? val[k] : add4(acc[k], val[k]);
-            }
-            if (jv == V - 1) {
-                float* o = p.out + ((((size_t)b * p.Xs + jx) * p.Y + jy) * p.Z + jz) * C;
-#pragma unroll
-                for (int k = 0; k < CPL; ++k) {
-                    const int c4 = lane + 32 * k;
-                    if (c4 < C4) {
-                        float4 r = acc[k];
-                        if (MODE == MVF_FUSE_MEAN) r = mul4(p.inv_v, r);
-                        if (p.bn_scale) {
-                            const float4 s = ldg4(p.bn_scale + 4 * c4), h = ldg4(p.bn_shift + 4 * c4);
-                            r = make_float4(fmaf(r.x, s.x, h.x), fmaf(r.y, s.y, h.y), fmaf(r.z, s.z, h.z), fmaf(r.w, s.w, h.w));
-                        }
-                        if (p.flags & MVF_FLAG_RELU_OUT) r = relu4(r);
-                        stcs4(o + 4 * c4, r);
-                    }
-                }
-            }
-        }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// Run kernel (production).  A warp owns L consecutive z-voxels of ONE (ix,iy) column for ONE
-// chunk of 128*CPL channels.  All L accumulators stay in registers across the whole view loop
-// (the per-view grids never exist), and the four taps of the current bilinear cell are cached in
-// registers: along a z-run the projected pixel moves ~0.3 px per voxel, so only about one step in
-// three changes cell and has to touch the load pipe at all.  On-chip load bandwidth (128 B/clk/SM
-// through L1), not HBM, is what bounds this op, so cutting tap loads is the lever.
-//   phase A (lanes = (view, z-step) pairs): voxel->pixel projection, floor, weights, validity and
-//           the "cell changed" flag, individually rounded fp32 (bit-exact vs the oracle), written
-//           to a 32-slot per-warp shared-memory table;
-//   phase B (lanes = float4 channel slots): walk the run; per step one broadcast LDS.128 of the
-//           four weights, a predicated patch reload (4 coalesced 128-bit read-only loads, 512 B
-//           per warp instruction) when the cell changed, and 16 FMAs straight into the accumulators.
-constexpr int RUN_WARPS = 8, RUN_TX = 4, RUN_TY = 2;
-
-// FULLC: C/4 is a multiple of 32*CPL, so no lane ever falls off the channel vector.
-//
-// What bounds this kernel is the register-return bandwidth of the load/store unit (128 B/clk/SM):
-// every byte a lane receives -- tap data, but also BROADCAST shared-memory reads -- crosses it.
-// So the per-step broadcast is kept to 8 bytes: ax = x1 - u and ay = y1 - w (two steps per
-// LDS.128); each lane forms bx = 1 - ax, by = 1 - ay and the four products itself (<= 1 ulp from
-// the reference's (u - x0), inside the 1e-5 feature tolerance; indices and validity masks stay
-// bit-exact, they come from phase A).  A reload reads one 32-bit word: the byte offset of the
-// cell's (y0,x0) tap with the complement of the 4 validity bits in its low nibble -- interior
-// cells (nibble 0) take the fast path with constant strides, border cells zero-fill per tap.
-template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC>
-__global__ void __launch_bounds__(RUN_WARPS * 32, (CPL * L <= 16) ? 2 : 1)
-unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
-    constexpr int VPP = 32 / L;                       // views handled per phase A
-    static_assert(VPP * L == 32 && (L % 2) == 0, "L must be even and divide 32");
-    __shared__ float sKR[MVF_MAX_VIEWS][12];
-    __shared__ float sOff[3];
-    __shared__ __align__(16) float2 sA[RUN_WARPS][32];   // (ax, ay) per (view, z-step) slot
-    __shared__ __align__(16) uint4 sO[RUN_WARPS][32];    // four tap byte offsets (clamped into the map); .x low nibble = ~valid bits
-
-    const int b = blockIdx.y / nchunk, chunk = blockIdx.y - b * nchunk;
-    const int tid = threadIdx.x;
-    const bool world = (p.flags & MVF_FLAG_WORLD_GRID) != 0;
-    if (tid < p.V) {
-        const float* P = p.Rcam + ((size_t)b * p.V + tid) * 12;
-        const float* K = p.Kmat + (size_t)b * 9;
-        const float* P0 = p.Rmain ? p.Rmain + (size_t)b * 12 : p.Rcam + (size_t)b * p.V * 12;
-        float Rinv[12], M[12];
-        inverse_pose(P, Rinv);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                M[i * 4 + j] = dot3_rn(K[i * 3 + 0], K[i * 3 + 1], K[i * 3 + 2],
-                                       Rinv[0 * 4 + j], Rinv[1 * 4 + j], Rinv[2 * 4 + j]);
-        if (world) {
-#pragma unroll
-            for (int e = 0; e < 12; ++e) sKR[tid][e] = M[e];
-        } else {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float t3 = (j == 3) ? 1.0f : 0.0f;
-                    sKR[tid][i * 4 + j] = dot4_rn(M[i * 4 + 0], M[i * 4 + 1], M[i * 4 + 2], M[i * 4 + 3],
-                                                  P0[0 * 4 + j], P0[1 * 4 + j], P0[2 * 4 + j], t3);
-                }
-        }
-    }
-    if (tid == 32 && world) {
-        const float* P0 = p.Rmain ? p.Rmain + (size_t)b * 12 : p.Rcam + (size_t)b * p.V * 12;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
             const float v = dot4_rn(P0[i * 4 + 0], P0[i * 4 + 1], P0[i * 4 + 2], P0[i * 4 + 3], 0.0f, 0.0f, p.grid_dist, 1.0f);
             sOff[i] = v;
             if (p.out_grid_pos && blockIdx.x == 0 && chunk == 0) p.out_grid_pos[b * 3 + i] = v;
@@ -299,13 +103,13 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
     const int tiles_z = (p.Z + L - 1) / L;
     const int tiles_y = (p.Y + RUN_TY - 1) / RUN_TY;
     int t = blockIdx.x;
-    const int tz = t % tiles_z; t /= tiles_z;
+    const int zpart = t % zsplit; t /= zsplit;
     const int ty = t % tiles_y; t /= tiles_y;
     const int warp = tid >> 5, lane = tid & 31;
     const int ixs = t * RUN_TX + (warp % RUN_TX);
     const int iy = ty * RUN_TY + (warp / RUN_TX);
-    const int z0 = tz * L;
     if (ixs >= p.Xs || iy >= p.Y) return;             // warp-uniform; no block-wide sync below
+    const int tz_begin = (int)(((long long)zpart * tiles_z) / zsplit), tz_end = (int)(((long long)(zpart + 1) * tiles_z) / zsplit);
     const unsigned FULL = 0xffffffffu;
 
     const int C = p.C, V = p.V, C4 = C >> 2;
@@ -317,30 +121,33 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
 #pragma unroll
     for (int c = 0; c < CPL; ++c) lane_off[c] = 16u * (unsigned)(FULLC ? (c4base + 32 * c) : min(c4base + 32 * c, C4 - 1));
     const float* feats_b = p.feats + (size_t)b * V * view_stride;
-    const long long strideX = 4ll * C, strideY = 4ll * C * p.fw;      // bytes between x / y neighbours
+    const unsigned CB = 4u * (unsigned)C;                              // bytes per tap vector
 
     float gxv = p.gx[p.x_begin + ixs], gyv = p.gy[iy];
     if (world) { gxv = add_rn(gxv, sOff[0]); gyv = add_rn(gyv, sOff[1]); }
+    const int sub_a = lane / L, k_a = lane - sub_a * L;               // phase A role of this lane
 
-    // accumulators and the cached bilinear patch live as packed fp32x2 pairs (FFMA2 operands)
     const ulonglong2 zz = make_ulonglong2(0ull, 0ull);
+    for (int tz = tz_begin; tz < tz_end; ++tz) {
+    const int z0 = tz * L;
+    // accumulators and the cached bilinear patch live as packed fp32x2 pairs (FFMA2 operands)
     ulonglong2 acc[L][CPL];
 #pragma unroll
     for (int k = 0; k < L; ++k)
 #pragma unroll
         for (int c = 0; c < CPL; ++c) acc[k][c] = zz;
-    ulonglong2 tA[CPL], tB[CPL], tC[CPL], tD[CPL];
+    ulonglong2 T00[CPL], T01[CPL], T10[CPL], T11[CPL];
 #pragma unroll
-    for (int c = 0; c < CPL; ++c) { tA[c] = zz; tB[c] = zz; tC[c] = zz; tD[c] = zz; }
+    for (int c = 0; c < CPL; ++c) { T00[c] = zz; T01[c] = zz; T10[c] = zz; T11[c] = zz; }
 
     for (int v0 = 0; v0 < V; v0 += VPP) {
         // ---- phase A: lane = (view v0 + lane / L, z-step lane % L)
-        unsigned rmask;
+        unsigned vmask, lm0, lm1, lm2, lm3;
         {
-            const int sub = lane / L, k = lane - sub * L;
-            const int v = v0 + sub, iz = z0 + k;
-            float ax = 0.f, ay = 0.f;
+            const int v = v0 + sub_a, iz = z0 + k_a;
+            float wx0 = 0.f, wy0 = 0.f;
             int bits = 0, x0 = INT32_MIN, y0 = INT32_MIN;
+            int row0 = 0, row1 = 0, col0 = 0, col1 = 0;
             if (v < V && iz < p.Z) {
                 float z = p.gz[iz];
                 if (world) z = add_rn(z, sOff[2]);
@@ -357,7 +164,14 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
                     const bool iny0 = (y0 >= 0) && (y0 < p.fh), iny1 = (y0 + 1 >= 0) && (y0 + 1 < p.fh);
                     bits = (int)(iny0 && inx0) | ((int)(iny1 && inx0) << 1) | ((int)(iny0 && inx1) << 2) |
                            ((int)(iny1 && inx1) << 3);
-                    if (bits) { ax = sub_rn((float)(x0 + 1), u); ay = sub_rn((float)(y0 + 1), w); }   // :214-217
+                    if (bits) {
+                        const int ox = x0 & 1, oy = y0 & 1;
+                        col0 = x0 + ox; col1 = x0 + 1 - ox;                  // the even / the odd column of {x0, x0+1}
+                        row0 = y0 + oy; row1 = y0 + 1 - oy;
+                        // weight of the tap column x0 is (x1 - u), of x0+1 it is (u - x0)   (:214-217)
+                        wx0 = ox ? sub_rn(u, x0f) : sub_rn((float)(x0 + 1), u);
+                        wy0 = oy ? sub_rn(w, y0f) : sub_rn((float)(y0 + 1), w);
+                    }
                 }
                 if (chunk == 0 && (p.out_idx || p.out_valid)) {
                     const size_t vox = (((size_t)b * V + v) * p.Xs + ixs) * p.Y * p.Z + (size_t)iy * p.Z + iz;
@@ -365,24 +179,32 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
                     if (p.out_valid) p.out_valid[vox] = (uint8_t)bits;
                 }
             }
-            // sampling state of this step: the cell, or "nothing" (-1).  The patch registers are
-            // refreshed whenever the state differs from the previous step's (always at a run start).
-            const int cell = bits ? (y0 * p.fw + x0) : INT32_MIN;
-            const int pcell = __shfl_up_sync(FULL, cell, 1), pbits = __shfl_up_sync(FULL, bits, 1);
-            const bool reload = (k == 0) || (cell != pcell) || (bits != pbits);   // bits: (y, fw-1) and (y+1, -1) share a cell id
-            rmask = __ballot_sync(FULL, reload);
-            sA[warp][lane] = make_float2(ax, ay);
-            // tap byte offsets, each clamped into the map so that every load is legal; the complement of the
-            // validity bits rides in the low nibble of .x (offsets are multiples of 16): a tap that is outside
-            // the map is zeroed after the load (TF-GPU gather_nd zero fill)
-            uint4 o4 = make_uint4(15u, 0u, 0u, 0u);
-            if (bits) {
-                const int xa = min(max(x0, 0), p.fw - 1), xb = min(max(x0 + 1, 0), p.fw - 1);
-                const int ya = min(max(y0, 0), p.fh - 1), yb = min(max(y0 + 1, 0), p.fh - 1);
-                const unsigned CB = 4u * (unsigned)C;
-                const unsigned oa = (unsigned)(ya * p.fw + xa) * CB;
-                const unsigned dX = (xb != xa) ? CB : 0u, dY = (yb != ya) ? (unsigned)p.fw * CB : 0u;
-                o4 = make_uint4(oa | (unsigned)(15 ^ bits), oa + dY, oa + dX, oa + dX + dY);
+            const bool valid = bits != 0;
+            // a slot is (re)loaded when the coordinate it has to hold differs from the previous step's
+            // (always at a run start and after a step that sampled nothing)
+            const int prow0 = __shfl_up_sync(FULL, row0, 1), prow1 = __shfl_up_sync(FULL, row1, 1);
+            const int pcol0 = __shfl_up_sync(FULL, col0, 1), pcol1 = __shfl_up_sync(FULL, col1, 1);
+            const bool pvalid = __shfl_up_sync(FULL, (int)valid, 1) != 0;
+            const bool first = (k_a == 0) || !pvalid;
+            const bool cr0 = first || row0 != prow0, cr1 = first || row1 != prow1;
+            const bool cc0 = first || col0 != pcol0, cc1 = first || col1 != pcol1;
+            vmask = __ballot_sync(FULL, valid);
+            lm0 = __ballot_sync(FULL, valid && (cr0 || cc0));
+            lm1 = __ballot_sync(FULL, valid && (cr0 || cc1));
+            lm2 = __ballot_sync(FULL, valid && (cr1 || cc0));
+            lm3 = __ballot_sync(FULL, valid && (cr1 || cc1));
+            sW[warp][lane] = make_float2(wx0, wy0);
+            // slot byte offsets, clamped into the map so that every load is legal; a slot whose coordinate is
+            // outside the map is zeroed after the load (TF-GPU gather_nd zero fill), flagged in the low nibble
+            // of .x (offsets are multiples of 16)
+            uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) {
+                const int r0c = min(max(row0, 0), p.fh - 1), r1c = min(max(row1, 0), p.fh - 1);
+                const int c0c = min(max(col0, 0), p.fw - 1), c1c = min(max(col1, 0), p.fw - 1);
+                const unsigned oob = (unsigned)(r0c != row0 || c0c != col0) | ((unsigned)(r0c != row0 || c1c != col1) << 1) |
+                                     ((unsigned)(r1c != row1 || c0c != col0) << 2) | ((unsigned)(r1c != row1 || c1c != col1) << 3);
+                o4 = make_uint4((unsigned)(r0c * p.fw + c0c) * CB | oob, (unsigned)(r0c * p.fw + c1c) * CB,
+                                (unsigned)(r1c * p.fw + c0c) * CB, (unsigned)(r1c * p.fw + c1c) * CB);
             }
             sO[warp][lane] = o4;
         }
@@ -393,46 +215,63 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
         for (int sub = 0; sub < VPP; ++sub) {
             const int vv = v0 + sub;
             if (vv >= V) break;
+            const unsigned vm = (vmask >> (sub * L)) & ((1u << L) - 1u);
+            if (PLAIN && vm == 0u) continue;                           // the whole run misses this view
+            const unsigned m0 = lm0 >> (sub * L), m1 = lm1 >> (sub * L), m2 = lm2 >> (sub * L), m3 = lm3 >> (sub * L);
+            const unsigned many = m0 | m1 | m2 | m3;
             // per-lane 64-bit base of this view; a tap address is base + warp-uniform byte offset
             const char* vb[CPL];
 #pragma unroll
             for (int c = 0; c < CPL; ++c) vb[c] = (const char*)(feats_b + (size_t)vv * view_stride) + lane_off[FULLC ? 0 : c];
-            const unsigned vmask = rmask >> (sub * L);
-            const float2* aslot = &sA[warp][sub * L];
+            const float2* wslot = &sW[warp][sub * L];
             const uint4* oslot = &sO[warp][sub * L];
-            float4 aa = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 ww = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int k = 0; k < L; ++k) {
-                if ((vmask >> k) & 1u) {                                   // warp-uniform
-                    const uint4 o = oslot[k];                              // broadcast LDS.128
+                const bool valid = (vm >> k) & 1u;                          // warp-uniform
+                if ((k & 1) == 0 && (!PLAIN || ((vm >> k) & 3u))) ww = *reinterpret_cast<const float4*>(wslot + k);   // broadcast LDS.128: two steps
+                if (PLAIN && !valid) continue;
+                if ((many >> k) & 1u) {
+                    const uint4 o = oslot[k];                               // broadcast LDS.128
                     const unsigned ox = o.x & ~15u;
+                    if ((m0 >> k) & 1u) {
 #pragma unroll
-                    for (int c = 0; c < CPL; ++c) {
-                        const char* q = FULLC ? vb[0] + 512 * c : vb[c];
-                        tA[c] = ldg2x2(q + ox); tB[c] = ldg2x2(q + o.y); tC[c] = ldg2x2(q + o.z); tD[c] = ldg2x2(q + o.w);
+                        for (int c = 0; c < CPL; ++c) T00[c] = ldg2x2((FULLC ? vb[0] + 512 * c : vb[c]) + ox);
                     }
-                    if (o.x & 15u) {                                       // rare: border cell / nothing sampled
+                    if ((m1 >> k) & 1u) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) T01[c] = ldg2x2((FULLC ? vb[0] + 512 * c : vb[c]) + o.y);
+                    }
+                    if ((m2 >> k) & 1u) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) T10[c] = ldg2x2((FULLC ? vb[0] + 512 * c : vb[c]) + o.z);
+                    }
+                    if ((m3 >> k) & 1u) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) T11[c] = ldg2x2((FULLC ? vb[0] + 512 * c : vb[c]) + o.w);
+                    }
+                    if (o.x & 15u) {                                        // rare: the cell straddles the map border
 #pragma unroll
                         for (int c = 0; c < CPL; ++c) {
-                            if (o.x & 1u) tA[c] = zz;
-                            if (o.x & 2u) tB[c] = zz;
-                            if (o.x & 4u) tC[c] = zz;
-                            if (o.x & 8u) tD[c] = zz;
+                            if (o.x & 1u) T00[c] = zz;
+                            if (o.x & 2u) T01[c] = zz;
+                            if (o.x & 4u) T10[c] = zz;
+                            if (o.x & 8u) T11[c] = zz;
                         }
                     }
                 }
-                if ((k & 1) == 0) aa = *reinterpret_cast<const float4*>(aslot + k);   // broadcast LDS.128: two steps
-                const float ax = (k & 1) ? aa.z : aa.x, ay = (k & 1) ? aa.w : aa.y;
-                const float bx = 1.0f - ax, by = 1.0f - ay;
-                const float wa = ax * ay, wb = ax * by, wc = bx * ay, wd = bx * by;
-                if (MODE != MVF_FUSE_NONE && MODE != MVF_FUSE_MAX && !RELU_IN) {
+                const float wx0 = (k & 1) ? ww.z : ww.x, wy0 = (k & 1) ? ww.w : ww.y;
+                const float wx1 = 1.0f - wx0, wy1 = 1.0f - wy0;
+                const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+                if (PLAIN) {
 #pragma unroll
                     for (int c = 0; c < CPL; ++c)                          // 8 FFMA2 = 16 fp32 FMAs
-                        acc[k][c] = fma2x2(wd, tD[c], fma2x2(wc, tC[c], fma2x2(wb, tB[c], fma2x2(wa, tA[c], acc[k][c]))));
+                        acc[k][c] = fma2x2(w11, T11[c], fma2x2(w10, T10[c], fma2x2(w01, T01[c], fma2x2(w00, T00[c], acc[k][c]))));
                 } else {
 #pragma unroll
                     for (int c = 0; c < CPL; ++c) {
-                        float4 val = unpack4(fma2x2(wd, tD[c], fma2x2(wc, tC[c], fma2x2(wb, tB[c], fma2x2(wa, tA[c], zz)))));
+                        float4 val = zero4();
+                        if (valid) val = unpack4(fma2x2(w11, T11[c], fma2x2(w10, T10[c], fma2x2(w01, T01[c], fma2x2(w00, T00[c], zz)))));
                         if (RELU_IN) val = relu4(val);
                         if (MODE == MVF_FUSE_NONE) {
                             if (z0 + k < p.Z && (FULLC || c4base + 32 * c < C4)) {
@@ -450,34 +289,36 @@ unproject_run_kernel(const __grid_constant__ UnprojParams p, int nchunk) {
         }
         __syncwarp();
     }
-    if (MODE == MVF_FUSE_NONE) return;
+    if (MODE != MVF_FUSE_NONE) {
 #pragma unroll
-    for (int k = 0; k < L; ++k) {
-        if (z0 + k >= p.Z) break;
-        float* o = p.out + ((((size_t)b * p.Xs + ixs) * p.Y + iy) * p.Z + z0 + k) * C;
+        for (int k = 0; k < L; ++k) {
+            if (z0 + k >= p.Z) break;
+            float* o = p.out + ((((size_t)b * p.Xs + ixs) * p.Y + iy) * p.Z + z0 + k) * C;
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const int c4 = c4base + 32 * c;
-            if (!FULLC && c4 >= C4) continue;
-            float4 r = unpack4(acc[k][c]);
-            if (MODE == MVF_FUSE_MEAN) r = mul4(p.inv_v, r);
-            if (p.bn_scale) {
-                const float4 s = ldg4(p.bn_scale + 4 * c4), h = ldg4(p.bn_shift + 4 * c4);
-                r = make_float4(fmaf(r.x, s.x, h.x), fmaf(r.y, s.y, h.y), fmaf(r.z, s.z, h.z), fmaf(r.w, s.w, h.w));
+            for (int c = 0; c < CPL; ++c) {
+                const int c4 = c4base + 32 * c;
+                if (!FULLC && c4 >= C4) continue;
+                float4 r = unpack4(acc[k][c]);
+                if (MODE == MVF_FUSE_MEAN) r = mul4(p.inv_v, r);
+                if (p.bn_scale) {
+                    const float4 s = ldg4(p.bn_scale + 4 * c4), h = ldg4(p.bn_shift + 4 * c4);
+                    r = make_float4(fmaf(r.x, s.x, h.x), fmaf(r.y, s.y, h.y), fmaf(r.z, s.z, h.z), fmaf(r.w, s.w, h.w));
+                }
+                if (p.flags & MVF_FLAG_RELU_OUT) r = relu4(r);
+                stcs4(o + 4 * c4, r);
             }
-            if (p.flags & MVF_FLAG_RELU_OUT) r = relu4(r);
-            stcs4(o + 4 * c4, r);
         }
     }
+    }   // z-tile loop
 }
 
 template <int CPL, int L, bool RELU_IN, bool FULLC>
-static int launch_run_mode(const UnprojParams& p, dim3 grid, int nchunk, cudaStream_t s) {
+static int launch_run_mode(const UnprojParams& p, dim3 grid, int nchunk, int zsplit, cudaStream_t s) {
     switch (p.mode) {
-        case MVF_FUSE_NONE: unproject_run_kernel<CPL, L, MVF_FUSE_NONE, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk); break;
-        case MVF_FUSE_SUM:  unproject_run_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk); break;
-        case MVF_FUSE_MEAN: unproject_run_kernel<CPL, L, MVF_FUSE_MEAN, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk); break;
-        case MVF_FUSE_MAX:  unproject_run_kernel<CPL, L, MVF_FUSE_MAX, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk); break;
+        case MVF_FUSE_NONE: unproject_slot_kernel<CPL, L, MVF_FUSE_NONE, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_SUM:  unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_MEAN: unproject_slot_kernel<CPL, L, MVF_FUSE_MEAN, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_MAX:  unproject_slot_kernel<CPL, L, MVF_FUSE_MAX, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
         default: return MVF_EINVAL;
     }
     count_launch();
@@ -489,25 +330,20 @@ static int launch_run(const UnprojParams& p, int B, cudaStream_t s) {
     const int C4 = p.C / 4;
     const int nchunk = (C4 + 32 * CPL - 1) / (32 * CPL);
     if ((long long)B * nchunk > 65535) return MVF_EUNSUPPORTED;
-    const int tiles = ((p.Xs + RUN_TX - 1) / RUN_TX) * ((p.Y + RUN_TY - 1) / RUN_TY) * ((p.Z + L - 1) / L);
-    dim3 grid(tiles, B * nchunk);
+    const int tiles_z = (p.Z + L - 1) / L;
+    const long long cols = (long long)((p.Xs + RUN_TX - 1) / RUN_TX) * ((p.Y + RUN_TY - 1) / RUN_TY);
+    // a CTA walks tiles_z / zsplit z-tiles of its 4x2 columns; split z only as far as needed to give every
+    // SM several CTAs (2 resident per SM, >= 4 waves)
+    static const int zs_env = [] { const char* e = getenv("MVF_K1_ZSPLIT"); return e ? atoi(e) : 0; }();
+    int zsplit = 1;
+    while (zsplit < tiles_z && cols * zsplit * B * nchunk < 148ll * 2 * 4) zsplit *= 2;
+    if (zs_env > 0) zsplit = zs_env;
+    if (zsplit > tiles_z) zsplit = tiles_z;
+    dim3 grid((unsigned)(cols * zsplit), B * nchunk);
     const bool fullc = (C4 % (32 * CPL)) == 0;
     const bool relu_in = (p.flags & MVF_FLAG_RELU_IN) != 0;
-    if (fullc) return relu_in ? launch_run_mode<CPL, L, true, true>(p, grid, nchunk, s) : launch_run_mode<CPL, L, false, true>(p, grid, nchunk, s);
-    return relu_in ? launch_run_mode<CPL, L, true, false>(p, grid, nchunk, s) : launch_run_mode<CPL, L, false, false>(p, grid, nchunk, s);
-}
-
-template <int CPL>
-static int launch_k1(const UnprojParams& p, dim3 grid, cudaStream_t s) {
-    switch (p.mode) {
-        case MVF_FUSE_NONE: unproject_fuse_kernel<CPL, MVF_FUSE_NONE><<<grid, K1_THREADS, 0, s>>>(p); break;
-        case MVF_FUSE_SUM:  unproject_fuse_kernel<CPL, MVF_FUSE_SUM><<<grid, K1_THREADS, 0, s>>>(p); break;
-        case MVF_FUSE_MEAN: unproject_fuse_kernel<CPL, MVF_FUSE_MEAN><<<grid, K1_THREADS, 0, s>>>(p); break;
-        case MVF_FUSE_MAX:  unproject_fuse_kernel<CPL, MVF_FUSE_MAX><<<grid, K1_THREADS, 0, s>>>(p); break;
-        default: return MVF_EINVAL;
-    }
-    count_launch();
-    return check_launch();
+    if (fullc) return relu_in ? launch_run_mode<CPL, L, true, true>(p, grid, nchunk, zsplit, s) : launch_run_mode<CPL, L, false, true>(p, grid, nchunk, zsplit, s);
+    return relu_in ? launch_run_mode<CPL, L, true, false>(p, grid, nchunk, zsplit, s) : launch_run_mode<CPL, L, false, false>(p, grid, nchunk, zsplit, s);
 }
 
 // Fill the voxel-centre arrays the way the reference's tf.range calls do.
@@ -559,20 +395,14 @@ extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const f
     p.sx = (float)((double)fw / (double)img_w);          // :154
     p.inv_v = 1.0f / (float)V;
     p.grid_dist = (float)grid_dist;
-    const int tiles = ((p.Xs + BRICK_X - 1) / BRICK_X) * ((p.Y + BRICK_Y - 1) / BRICK_Y) * ((p.Z + BRICK_Z - 1) / BRICK_Z);
-    dim3 grid(tiles, B);
     cudaStream_t s = (cudaStream_t)stream;
     const int C4 = C / 4;
-    // Default: the run kernel; one warp covers 256 channels x 8 z-steps when C is a multiple of 256 (the FPN
-    // width), else 128 channels x 16 z-steps.  MVF_K1_VARIANT (debug / A-B measurement) overrides:
-    // 0 = first-generation brick kernel, 1 = run 128ch x 16, 2 = run 256ch x 8, 3 = run 128ch x 8.
+    // One warp covers 256 channels x 8 z-steps when C is a multiple of 256 (the FPN width), else
+    // 128 channels x 16 z-steps.  MVF_K1_VARIANT (debug / A-B measurement) overrides:
+    // 1 = 128ch x 16, 2 = 256ch x 8, 3 = 128ch x 8.
     static const int variant = [] { const char* e = getenv("MVF_K1_VARIANT"); return e ? atoi(e) : -1; }();
-    if (variant < 0) return (C4 % 64 == 0) ? launch_run<2, 8>(p, B, s) : launch_run<1, 16>(p, B, s);
     if (variant == 1) return launch_run<1, 16>(p, B, s);
     if (variant == 2) return launch_run<2, 8>(p, B, s);
     if (variant == 3) return launch_run<1, 8>(p, B, s);
-    if (C4 <= 32) return launch_k1<1>(p, grid, s);
-    if (C4 <= 64) return launch_k1<2>(p, grid, s);
-    if (C4 <= 128) return launch_k1<4>(p, grid, s);
-    return launch_k1<8>(p, grid, s);
+    return (C4 % 64 == 0) ? launch_run<2, 8>(p, B, s) : launch_run<1, 16>(p, B, s);
 }
