@@ -55,6 +55,7 @@ __device__ __forceinline__ bool usable_coord(float v) {
     return (fabsf(v) < 1073741824.0f);      // finite and |v| < 2^30 (NaN compares false)
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stcs4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -75,6 +76,10 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f3
 __device__ __forceinline__ u64 dup2(float w) { u64 d; asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(w)); return d; }   // folds into FFMA2's scalar operand
 __device__ __forceinline__ u64 pack2(float a, float b) { u64 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b)); return d; }
 __device__ __forceinline__ float2 unpack2(u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float lo2(u64 v) { return unpack2(v).x; }
+__device__ __forceinline__ float hi2(u64 v) { return unpack2(v).y; }
 __device__ __forceinline__ ulonglong2 ldg2x2(const void* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); }
 // acc + w * t for four channels held as two packed pairs
 __device__ __forceinline__ ulonglong2 fma2x2(float w, ulonglong2 t, ulonglong2 a) {

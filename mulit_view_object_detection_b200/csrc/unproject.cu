@@ -47,7 +47,7 @@ struct UnprojParams {
 //   phase B (lanes = float4 channel slots): walk the run.
 constexpr int RUN_WARPS = 8, RUN_TX = 4, RUN_TY = 2;
 
-template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC>
+template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC, int PF_MODE>
 __global__ void __launch_bounds__(RUN_WARPS * 32, (CPL * L <= 16) ? 2 : 1)
 unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zsplit) {
     constexpr int VPP = 32 / L;                       // views handled per phase A
@@ -55,7 +55,9 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
     static_assert(VPP * L == 32 && (L % 2) == 0, "L must be even and divide 32");
     __shared__ float sKR[MVF_MAX_VIEWS][12];
     __shared__ float sOff[3];
-    __shared__ __align__(16) float2 sW[RUN_WARPS][32];   // (weight of slot column 0, weight of slot row 0) per (view, z-step)
+    // weights of slot column 0 / slot row 0, stored per STEP PAIR as (wx0[k], wx0[k+1], wy0[k], wy0[k+1]) so that one
+    // broadcast LDS.128 serves two steps and the lanes form both steps' products with packed fp32x2 ops
+    __shared__ __align__(16) float sW[RUN_WARPS][64];
     __shared__ __align__(16) uint4 sO[RUN_WARPS][32];    // byte offsets of slots 00,01,10,11 (clamped into the map); .x low nibble = out-of-map bits
 
     const int b = blockIdx.y / nchunk, chunk = blockIdx.y - b * nchunk;
@@ -126,6 +128,12 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
     float gxv = p.gx[p.x_begin + ixs], gyv = p.gy[iy];
     if (world) { gxv = add_rn(gxv, sOff[0]); gyv = add_rn(gyv, sOff[1]); }
     const int sub_a = lane / L, k_a = lane - sub_a * L;               // phase A role of this lane
+    constexpr unsigned LMASK = (1u << L) - 1u;
+    // byte distance of the lane's c-th channel slot from its first (a compile-time constant when FULLC)
+    auto coff = [&](int c) -> int { return FULLC ? 512 * c : (int)(lane_off[c] - lane_off[0]); };
+    const size_t view_bytes = view_stride * sizeof(float);
+    const char* vbase = (const char*)feats_b + lane_off[0];
+    const bool has_bn = p.bn_scale != nullptr, relu_out = (p.flags & MVF_FLAG_RELU_OUT) != 0;
 
     const ulonglong2 zz = make_ulonglong2(0ull, 0ull);
     for (int tz = tz_begin; tz < tz_end; ++tz) {
@@ -193,7 +201,10 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
             lm1 = __ballot_sync(FULL, valid && (cr0 || cc1));
             lm2 = __ballot_sync(FULL, valid && (cr1 || cc0));
             lm3 = __ballot_sync(FULL, valid && (cr1 || cc1));
-            sW[warp][lane] = make_float2(wx0, wy0);
+            {
+                float* wp = &sW[warp][sub_a * (2 * L) + (k_a >> 1) * 4 + (k_a & 1)];
+                wp[0] = wx0; wp[2] = wy0;
+            }
             // slot byte offsets, clamped into the map so that every load is legal; a slot whose coordinate is
             // outside the map is zeroed after the load (TF-GPU gather_nd zero fill), flagged in the low nibble
             // of .x (offsets are multiples of 16)
@@ -207,48 +218,67 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
                                 (unsigned)(r1c * p.fw + c0c) * CB, (unsigned)(r1c * p.fw + c1c) * CB);
             }
             sO[warp][lane] = o4;
+            // L1 prefetch of the tap lines this step will load: the lanes of phase A know the addresses one
+            // whole view-loop ahead of the lanes of phase B
+            if (PF_MODE != 0 && valid) {
+                const char* tb = (const char*)(feats_b + (size_t)(v0 + sub_a) * view_stride) + (size_t)chunk * (512 * CPL);
+                const bool f0 = (PF_MODE == 2) ? (cr0 || cc0) : first, f1 = (PF_MODE == 2) ? (cr0 || cc1) : first;
+                const bool f2 = (PF_MODE == 2) ? (cr1 || cc0) : first, f3 = (PF_MODE == 2) ? (cr1 || cc1) : first;
+#pragma unroll
+                for (int ln = 0; ln < 4 * CPL; ++ln) {
+                    if (f0) prefetch_l1(tb + (o4.x & ~15u) + 128 * ln);
+                    if (f1) prefetch_l1(tb + o4.y + 128 * ln);
+                    if (f2) prefetch_l1(tb + o4.z + 128 * ln);
+                    if (f3) prefetch_l1(tb + o4.w + 128 * ln);
+                }
+            }
         }
         __syncwarp();
         // ---- phase B: lanes = float4 channel slots.  The view loop stays ROLLED (only the L z-steps are
         // unrolled, they index the accumulator registers): the hot loop must fit the instruction cache.
+        const char* vptr = vbase + (size_t)v0 * view_bytes;                 // per-lane base of view v0 (+ channel slot)
 #pragma unroll 1
-        for (int sub = 0; sub < VPP; ++sub) {
+        for (int sub = 0; sub < VPP && v0 + sub < V; ++sub, vptr += view_bytes) {
             const int vv = v0 + sub;
-            if (vv >= V) break;
-            const unsigned vm = (vmask >> (sub * L)) & ((1u << L) - 1u);
+            const unsigned vm = (vmask >> (sub * L)) & LMASK;
             if (PLAIN && vm == 0u) continue;                           // the whole run misses this view
-            const unsigned m0 = lm0 >> (sub * L), m1 = lm1 >> (sub * L), m2 = lm2 >> (sub * L), m3 = lm3 >> (sub * L);
-            const unsigned many = m0 | m1 | m2 | m3;
-            // per-lane 64-bit base of this view; a tap address is base + warp-uniform byte offset
-            const char* vb[CPL];
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) vb[c] = (const char*)(feats_b + (size_t)vv * view_stride) + lane_off[FULLC ? 0 : c];
-            const float2* wslot = &sW[warp][sub * L];
+            // reload flags of this view: slots 00 | 01 in mlo, 10 | 11 in mhi (bit k / bit L+k)
+            unsigned mlo = ((lm0 >> (sub * L)) & LMASK) | (((lm1 >> (sub * L)) & LMASK) << L);
+            unsigned mhi = ((lm2 >> (sub * L)) & LMASK) | (((lm3 >> (sub * L)) & LMASK) << L);
+            unsigned many = mlo | mhi;
+            // pin the three words in registers: every per-step test below is then ONE LOP3 against a constant
+            // (left alone, ptxas re-derives them from the ballots with shifts at every use)
+            asm volatile("" : "+r"(mlo), "+r"(mhi), "+r"(many));
+            const float4* wslot = reinterpret_cast<const float4*>(&sW[warp][sub * (2 * L)]);
             const uint4* oslot = &sO[warp][sub * L];
-            float4 ww = make_float4(0.f, 0.f, 0.f, 0.f);
+            u64 w00p = 0, w01p = 0, w10p = 0, w11p = 0;                // slot weights of steps (k, k+1), packed
 #pragma unroll
             for (int k = 0; k < L; ++k) {
                 const bool valid = (vm >> k) & 1u;                          // warp-uniform
-                if ((k & 1) == 0 && (!PLAIN || ((vm >> k) & 3u))) ww = *reinterpret_cast<const float4*>(wslot + k);   // broadcast LDS.128: two steps
+                if ((k & 1) == 0 && (!PLAIN || ((vm >> k) & 3u))) {
+                    const float4 ww = wslot[k >> 1];                        // broadcast LDS.128: two steps
+                    const u64 X0 = pack2(ww.x, ww.y), Y0 = pack2(ww.z, ww.w), ONE = pack2(1.0f, 1.0f);
+                    const u64 X1 = sub2(ONE, X0), Y1 = sub2(ONE, Y0);
+                    w00p = mul2(Y0, X0); w01p = mul2(Y0, X1); w10p = mul2(Y1, X0); w11p = mul2(Y1, X1);
+                }
                 if (PLAIN && !valid) continue;
-                if ((many >> k) & 1u) {
+                if (many & ((1u << k) | (1u << (L + k)))) {
                     const uint4 o = oslot[k];                               // broadcast LDS.128
-                    const unsigned ox = o.x & ~15u;
-                    if ((m0 >> k) & 1u) {
+                    if (mlo & (1u << k)) {
 #pragma unroll
-                        for (int c = 0; c < CPL; ++c) T00[c] = ldg2x2((FULLC ? vb[0] + 512 * c : vb[c]) + ox);
+                        for (int c = 0; c < CPL; ++c) T00[c] = ldg2x2(vptr + coff(c) + (o.x & ~15u));
                     }
-                    if ((m1 >> k) & 1u) {
+                    if (mlo & (1u << (L + k))) {
 #pragma unroll
-                        for (int c = 0; c < CPL; ++c) T01[c] = ldg2x2((FULLC ? vb[0] + 512 * c : vb[c]) + o.y);
+                        for (int c = 0; c < CPL; ++c) T01[c] = ldg2x2(vptr + coff(c) + o.y);
                     }
-                    if ((m2 >> k) & 1u) {
+                    if (mhi & (1u << k)) {
 #pragma unroll
-                        for (int c = 0; c < CPL; ++c) T10[c] = ldg2x2((FULLC ? vb[0] + 512 * c : vb[c]) + o.z);
+                        for (int c = 0; c < CPL; ++c) T10[c] = ldg2x2(vptr + coff(c) + o.z);
                     }
-                    if ((m3 >> k) & 1u) {
+                    if (mhi & (1u << (L + k))) {
 #pragma unroll
-                        for (int c = 0; c < CPL; ++c) T11[c] = ldg2x2((FULLC ? vb[0] + 512 * c : vb[c]) + o.w);
+                        for (int c = 0; c < CPL; ++c) T11[c] = ldg2x2(vptr + coff(c) + o.w);
                     }
                     if (o.x & 15u) {                                        // rare: the cell straddles the map border
 #pragma unroll
@@ -260,9 +290,8 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
                         }
                     }
                 }
-                const float wx0 = (k & 1) ? ww.z : ww.x, wy0 = (k & 1) ? ww.w : ww.y;
-                const float wx1 = 1.0f - wx0, wy1 = 1.0f - wy0;
-                const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
+                const float w00 = (k & 1) ? hi2(w00p) : lo2(w00p), w01 = (k & 1) ? hi2(w01p) : lo2(w01p);
+                const float w10 = (k & 1) ? hi2(w10p) : lo2(w10p), w11 = (k & 1) ? hi2(w11p) : lo2(w11p);
                 if (PLAIN) {
 #pragma unroll
                     for (int c = 0; c < CPL; ++c)                          // 8 FFMA2 = 16 fp32 FMAs
@@ -290,22 +319,20 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
         __syncwarp();
     }
     if (MODE != MVF_FUSE_NONE) {
+        float* obase = p.out + ((((size_t)b * p.Xs + ixs) * p.Y + iy) * p.Z + z0) * C + 4 * c4base;
 #pragma unroll
-        for (int k = 0; k < L; ++k) {
-            if (z0 + k >= p.Z) break;
-            float* o = p.out + ((((size_t)b * p.Xs + ixs) * p.Y + iy) * p.Z + z0 + k) * C;
+        for (int c = 0; c < CPL; ++c) {
+            if (!FULLC && c4base + 32 * c >= C4) continue;
+            float4 bs = make_float4(1.f, 1.f, 1.f, 1.f), bh = zero4();
+            if (has_bn) { bs = ldg4(p.bn_scale + 4 * (c4base + 32 * c)); bh = ldg4(p.bn_shift + 4 * (c4base + 32 * c)); }
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const int c4 = c4base + 32 * c;
-                if (!FULLC && c4 >= C4) continue;
+            for (int k = 0; k < L; ++k) {
+                if (z0 + k >= p.Z) break;
                 float4 r = unpack4(acc[k][c]);
                 if (MODE == MVF_FUSE_MEAN) r = mul4(p.inv_v, r);
-                if (p.bn_scale) {
-                    const float4 s = ldg4(p.bn_scale + 4 * c4), h = ldg4(p.bn_shift + 4 * c4);
-                    r = make_float4(fmaf(r.x, s.x, h.x), fmaf(r.y, s.y, h.y), fmaf(r.z, s.z, h.z), fmaf(r.w, s.w, h.w));
-                }
-                if (p.flags & MVF_FLAG_RELU_OUT) r = relu4(r);
-                stcs4(o + 4 * c4, r);
+                if (has_bn) r = make_float4(fmaf(r.x, bs.x, bh.x), fmaf(r.y, bs.y, bh.y), fmaf(r.z, bs.z, bh.z), fmaf(r.w, bs.w, bh.w));
+                if (relu_out) r = relu4(r);
+                stcs4(obase + (size_t)k * C + 128 * c, r);
             }
         }
     }
@@ -315,10 +342,16 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
 template <int CPL, int L, bool RELU_IN, bool FULLC>
 static int launch_run_mode(const UnprojParams& p, dim3 grid, int nchunk, int zsplit, cudaStream_t s) {
     switch (p.mode) {
-        case MVF_FUSE_NONE: unproject_slot_kernel<CPL, L, MVF_FUSE_NONE, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
-        case MVF_FUSE_SUM:  unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
-        case MVF_FUSE_MEAN: unproject_slot_kernel<CPL, L, MVF_FUSE_MEAN, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
-        case MVF_FUSE_MAX:  unproject_slot_kernel<CPL, L, MVF_FUSE_MAX, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_NONE: unproject_slot_kernel<CPL, L, MVF_FUSE_NONE, RELU_IN, FULLC, 0><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_SUM: {
+            static const int pf = [] { const char* e = getenv("MVF_K1_PF"); return e ? atoi(e) : 0; }();
+            if (pf == 1) unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC, 1><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit);
+            else if (pf == 2) unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC, 2><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit);
+            else unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC, 0><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit);
+            break;
+        }
+        case MVF_FUSE_MEAN: unproject_slot_kernel<CPL, L, MVF_FUSE_MEAN, RELU_IN, FULLC, 0><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_MAX:  unproject_slot_kernel<CPL, L, MVF_FUSE_MAX, RELU_IN, FULLC, 0><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
         default: return MVF_EINVAL;
     }
     count_launch();
