@@ -55,9 +55,8 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
     static_assert(VPP * L == 32 && (L % 2) == 0, "L must be even and divide 32");
     __shared__ float sKR[MVF_MAX_VIEWS][12];
     __shared__ float sOff[3];
-    // weights of slot column 0 / slot row 0, stored per STEP PAIR as (wx0[k], wx0[k+1], wy0[k], wy0[k+1]) so that one
-    // broadcast LDS.128 serves two steps and the lanes form both steps' products with packed fp32x2 ops
-    __shared__ __align__(16) float sW[RUN_WARPS][64];
+    // the four slot weights (w00, w01, w10, w11) of every (view, z-step); a slot outside the map has weight 0
+    __shared__ __align__(16) float4 sW[RUN_WARPS][32];
     __shared__ __align__(16) uint4 sO[RUN_WARPS][32];    // byte offsets of slots 00,01,10,11 (clamped into the map); .x low nibble = out-of-map bits
 
     const int b = blockIdx.y / nchunk, chunk = blockIdx.y - b * nchunk;
@@ -153,7 +152,7 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
         unsigned vmask, lm0, lm1, lm2, lm3;
         {
             const int v = v0 + sub_a, iz = z0 + k_a;
-            float wx0 = 0.f, wy0 = 0.f;
+            float4 w4 = zero4();
             int bits = 0, x0 = INT32_MIN, y0 = INT32_MIN;
             int row0 = 0, row1 = 0, col0 = 0, col1 = 0;
             if (v < V && iz < p.Z) {
@@ -176,9 +175,13 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
                         const int ox = x0 & 1, oy = y0 & 1;
                         col0 = x0 + ox; col1 = x0 + 1 - ox;                  // the even / the odd column of {x0, x0+1}
                         row0 = y0 + oy; row1 = y0 + 1 - oy;
-                        // weight of the tap column x0 is (x1 - u), of x0+1 it is (u - x0)   (:214-217)
-                        wx0 = ox ? sub_rn(u, x0f) : sub_rn((float)(x0 + 1), u);
-                        wy0 = oy ? sub_rn(w, y0f) : sub_rn((float)(y0 + 1), w);
+                        // weight of the tap column x0 is (x1 - u), of x0+1 it is (u - x0); a column / row outside
+                        // the map gets weight 0 = the zero fill of TF-GPU gather_nd   (:209-219)
+                        const float wxa = inx0 ? sub_rn((float)(x0 + 1), u) : 0.f, wxb = inx1 ? sub_rn(u, x0f) : 0.f;
+                        const float wya = iny0 ? sub_rn((float)(y0 + 1), w) : 0.f, wyb = iny1 ? sub_rn(w, y0f) : 0.f;
+                        const float wx0 = ox ? wxb : wxa, wx1 = ox ? wxa : wxb;
+                        const float wy0 = oy ? wyb : wya, wy1 = oy ? wya : wyb;
+                        w4 = make_float4(mul_rn(wy0, wx0), mul_rn(wy0, wx1), mul_rn(wy1, wx0), mul_rn(wy1, wx1));
                     }
                 }
                 if (chunk == 0 && (p.out_idx || p.out_valid)) {
@@ -201,10 +204,7 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
             lm1 = __ballot_sync(FULL, valid && (cr0 || cc1));
             lm2 = __ballot_sync(FULL, valid && (cr1 || cc0));
             lm3 = __ballot_sync(FULL, valid && (cr1 || cc1));
-            {
-                float* wp = &sW[warp][sub_a * (2 * L) + (k_a >> 1) * 4 + (k_a & 1)];
-                wp[0] = wx0; wp[2] = wy0;
-            }
+            sW[warp][lane] = w4;
             // slot byte offsets, clamped into the map so that every load is legal; a slot whose coordinate is
             // outside the map is zeroed after the load (TF-GPU gather_nd zero fill), flagged in the low nibble
             // of .x (offsets are multiples of 16)
@@ -212,9 +212,7 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
             if (valid) {
                 const int r0c = min(max(row0, 0), p.fh - 1), r1c = min(max(row1, 0), p.fh - 1);
                 const int c0c = min(max(col0, 0), p.fw - 1), c1c = min(max(col1, 0), p.fw - 1);
-                const unsigned oob = (unsigned)(r0c != row0 || c0c != col0) | ((unsigned)(r0c != row0 || c1c != col1) << 1) |
-                                     ((unsigned)(r1c != row1 || c0c != col0) << 2) | ((unsigned)(r1c != row1 || c1c != col1) << 3);
-                o4 = make_uint4((unsigned)(r0c * p.fw + c0c) * CB | oob, (unsigned)(r0c * p.fw + c1c) * CB,
+                o4 = make_uint4((unsigned)(r0c * p.fw + c0c) * CB, (unsigned)(r0c * p.fw + c1c) * CB,
                                 (unsigned)(r1c * p.fw + c0c) * CB, (unsigned)(r1c * p.fw + c1c) * CB);
             }
             sO[warp][lane] = o4;
@@ -249,24 +247,20 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
             // pin the three words in registers: every per-step test below is then ONE LOP3 against a constant
             // (left alone, ptxas re-derives them from the ballots with shifts at every use)
             asm volatile("" : "+r"(mlo), "+r"(mhi), "+r"(many));
-            const float4* wslot = reinterpret_cast<const float4*>(&sW[warp][sub * (2 * L)]);
+            const float4* wslot = &sW[warp][sub * L];
             const uint4* oslot = &sO[warp][sub * L];
-            u64 w00p = 0, w01p = 0, w10p = 0, w11p = 0;                // slot weights of steps (k, k+1), packed
+            float4 wn = wslot[0];                                      // weights travel one step ahead of their use
 #pragma unroll
             for (int k = 0; k < L; ++k) {
                 const bool valid = (vm >> k) & 1u;                          // warp-uniform
-                if ((k & 1) == 0 && (!PLAIN || ((vm >> k) & 3u))) {
-                    const float4 ww = wslot[k >> 1];                        // broadcast LDS.128: two steps
-                    const u64 X0 = pack2(ww.x, ww.y), Y0 = pack2(ww.z, ww.w), ONE = pack2(1.0f, 1.0f);
-                    const u64 X1 = sub2(ONE, X0), Y1 = sub2(ONE, Y0);
-                    w00p = mul2(Y0, X0); w01p = mul2(Y0, X1); w10p = mul2(Y1, X0); w11p = mul2(Y1, X1);
-                }
+                const float4 ww = wn;
+                if (k + 1 < L) wn = wslot[k + 1];                           // broadcast LDS.128
                 if (PLAIN && !valid) continue;
                 if (many & ((1u << k) | (1u << (L + k)))) {
                     const uint4 o = oslot[k];                               // broadcast LDS.128
                     if (mlo & (1u << k)) {
 #pragma unroll
-                        for (int c = 0; c < CPL; ++c) T00[c] = ldg2x2(vptr + coff(c) + (o.x & ~15u));
+                        for (int c = 0; c < CPL; ++c) T00[c] = ldg2x2(vptr + coff(c) + o.x);
                     }
                     if (mlo & (1u << (L + k))) {
 #pragma unroll
@@ -280,18 +274,8 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
 #pragma unroll
                         for (int c = 0; c < CPL; ++c) T11[c] = ldg2x2(vptr + coff(c) + o.w);
                     }
-                    if (o.x & 15u) {                                        // rare: the cell straddles the map border
-#pragma unroll
-                        for (int c = 0; c < CPL; ++c) {
-                            if (o.x & 1u) T00[c] = zz;
-                            if (o.x & 2u) T01[c] = zz;
-                            if (o.x & 4u) T10[c] = zz;
-                            if (o.x & 8u) T11[c] = zz;
-                        }
-                    }
                 }
-                const float w00 = (k & 1) ? hi2(w00p) : lo2(w00p), w01 = (k & 1) ? hi2(w01p) : lo2(w01p);
-                const float w10 = (k & 1) ? hi2(w10p) : lo2(w10p), w11 = (k & 1) ? hi2(w11p) : lo2(w11p);
+                const float w00 = ww.x, w01 = ww.y, w10 = ww.z, w11 = ww.w;
                 if (PLAIN) {
 #pragma unroll
                     for (int c = 0; c < CPL; ++c)                          // 8 FFMA2 = 16 fp32 FMAs
