@@ -112,6 +112,19 @@ int mvf_convlstm_step(const float* x, const float* h_prev, const float* c_prev,
                       int B, int X, int Y, int Z, int C, int F, int flags,
                       float* h_out, float* c_out, void* stream);
 
+/* ---- ConvLSTM cell step on the tensor cores (tcgen05, 3xTF32 split) ------------------------------
+ * Same contract as mvf_convlstm_step (recurrent.py:442-479) for C % 32 == 0 and F % 64 == 0
+ * (MVF_EUNSUPPORTED otherwise: use mvf_convlstm_step).  Weights are prepared once per weight tensor:
+ *   mvf_convlstm_prepare(W [3,3,3,C+F,4F]) -> wsplit (mvf_convlstm_wsplit_bytes): K-major hi/lo halves,
+ *   the four gates of each 64-filter group adjacent.
+ * ws: mvf_convlstm_tc_workspace_bytes(...) bytes of device scratch (hi/lo halves of x and h_prev). */
+size_t mvf_convlstm_wsplit_bytes(int C, int F);
+int mvf_convlstm_prepare(const float* W, int C, int F, float* wsplit, void* stream);
+size_t mvf_convlstm_tc_workspace_bytes(int B, int X, int Y, int Z, int C, int F);
+int mvf_convlstm_step_tc(const float* x, const float* h_prev, const float* c_prev, const float* wsplit,
+                         const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
+                         int flags, float* h_out, float* c_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K3: proj_grid ---------------------------------------------------------------------------
  * replaces proj_grid([grid,Rcam,Kmat], config, proj_size)  model_multi.py:231-322 + nearest3 :357-369
  * grid [B,Xs,Y,Z,C] (slab [x_begin, x_begin+x_count) of the full grid; x_count==0 -> whole)

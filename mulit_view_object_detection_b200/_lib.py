@@ -49,6 +49,10 @@ _SIGS = {
     "mvf_view_reduce": (_i, [_p, _i, _i, _ll, _i, _i, _i, _p, _p, _p, _p]),
     "mvf_ident_fuse": (_i, [_p, _p, _p, _p, _p, _i, _i, _ll, _i, _i, _p, _p]),
     "mvf_convlstm_step": (_i, [_p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "mvf_convlstm_wsplit_bytes": (_sz, [_i, _i]),
+    "mvf_convlstm_prepare": (_i, [_p, _i, _i, _p, _p]),
+    "mvf_convlstm_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "mvf_convlstm_step_tc": (_i, [_p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "mvf_project_rays": (_i, [_p, _p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _p]),
     "mvf_project_depth_collapse": (_i, [_p, _p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i,
                                         _p, _f, _f, _f, _p, _p]),

@@ -1,0 +1,425 @@
+// K2  ConvLSTM gates on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Replaces ConvLSTMCell.call  mrcnn/recurrent.py:442-479:
+//     y = conv3d_SAME([x ; h_prev], W) + b      W [3,3,3,C+F,4F]   (recurrent.py:423-431, :453-459)
+//     j,i,f,o = split(y)  ;  c = c_prev*sig(f + forget_bias) + sig(i)*tanh(j)  ;  h = tanh(c)*sig(o)   (:460-477)
+//
+// Implicit GEMM:  M = voxels, N = 4F, K = 27*(C+F).  One CTA owns a 128-voxel box (BX x BY x BZ,
+// z fastest) and 64 filters x 4 gates = 256 accumulator columns in TMEM, so the gate
+// non-linearities run in the epilogue on values that never leave the SM.
+//   * A operand: for tap (dx,dy,dz) and a 32-channel chunk the 128 x 32 fp32 tile is ONE 5-D TMA box
+//     load of the channel-last tensor [B,X,Y,Z,C] at coordinates shifted by the tap; coordinates
+//     outside the grid are zero-filled by the TMA unit, which IS the conv's SAME padding -- no
+//     im2col, no halo logic, no per-element predicates.  The box lands in the 128-byte-swizzled
+//     K-major layout tcgen05.mma reads directly.
+//   * B operand: the weights, transposed once to K-major [4F, 27*(C+F)] with the four gates of a
+//     64-filter group adjacent (mvf_convlstm_prepare), 256 x 32 tile per chunk, 2-D TMA.
+//   * fp32 parity: the reference convolves in fp32; a plain TF32 MMA (10-bit mantissa) is 1e-3
+//     off.  Operands are split a = a_hi + a_lo (a_hi = the top 19 bits, exact in TF32) and three
+//     MMAs  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  accumulate in fp32 TMEM: ~2^-21 per product.
+//     a_hi / a_lo of the activations are produced by a tiny elementwise pass (which also applies the
+//     ReLU of model_multi.py:459), b_hi / b_lo once per weight tensor.
+//   * accumulation: TMEM adds truncate (measured: the error of one long chain grows linearly with K and is
+//     biased toward zero, 1.2e-4 at K = 13 824), so the chain is cut every `promote` K-chunks: the epilogue
+//     warps add the partial accumulator into a MASTER accumulator (second half of TMEM) with
+//     round-to-nearest fp32 adds (tcgen05.ld -> FADD -> tcgen05.st) and the MMAs restart from zero.
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
+//     allocator, warps 4-7 = epilogue (tcgen05.ld -> gates -> c/h stores).  2-stage smem ring
+//     (96 KB per stage: A_hi, A_lo, B_hi, B_lo), full/empty mbarriers, tcgen05.commit.
+#include <cuda.h>
+#include <stdlib.h>
+#include "mvf_common.cuh"
+
+namespace mvf {
+
+constexpr int TC_M = 128, TC_N = 256, TC_K = 32, TC_STAGES = 2, TC_THREADS = 256;
+constexpr int TC_FPT = 64;                                   // filters per CTA tile (x 4 gates = TC_N)
+constexpr uint32_t TC_A_BYTES = TC_M * TC_K * 4;             // 16 KB
+constexpr uint32_t TC_B_BYTES = TC_N * TC_K * 4;             // 32 KB
+constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;
+constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+struct TcArgs {
+    const float* bias; const float* c_prev; float* h_out; float* c_out;
+    int B, X, Y, Z, C, F;
+    int BX, BY, BZ, tiles_x, tiles_y, tiles_z;
+    int has_h;
+    int promote;                  // K-chunks per promotion of the partial accumulator into the master (0 = never)
+    float forget_bias;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 :: "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows at a 128 B pitch, 8-row atoms 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major), bits [16,30)
+    d |= (uint64_t)(1024u >> 4) << 32;                      // stride byte offset = 1024 B, bits [32,46)
+    d |= (uint64_t)1 << 46;                                 // descriptor version 1 (Blackwell), bits [46,48)
+    d |= (uint64_t)2 << 61;                                 // layout type SWIZZLE_128B, bits [61,64)
+    return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=256 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                    "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                    "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                    "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
+                   const __grid_constant__ CUtensorMap tm_hh, const __grid_constant__ CUtensorMap tm_hl,
+                   const __grid_constant__ CUtensorMap tm_wh, const __grid_constant__ CUtensorMap tm_wl,
+                   const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;              // swizzle-128B tiles need 1024 B alignment
+    const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+    const uint32_t part_full = bar_base + 8u * (2 * TC_STAGES);                    // MMA -> epilogue: a partial accumulator is complete
+    const uint32_t part_empty = bar_base + 8u * (2 * TC_STAGES + 1);               // epilogue -> MMA: it has been added into the master
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 2);                // the allocator writes the TMEM base address here
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates: blockIdx.x -> (b, tx, ty, tz) box of BX x BY x BZ voxels, blockIdx.y -> 64-filter group
+    int t = blockIdx.x;
+    const int tz = t % a.tiles_z; t /= a.tiles_z;
+    const int ty = t % a.tiles_y; t /= a.tiles_y;
+    const int tx = t % a.tiles_x; const int b = t / a.tiles_x;
+    const int x0 = tx * a.BX, y0 = ty * a.BY, z0 = tz * a.BZ;
+    const int ntile = blockIdx.y;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(part_full, 1); mbar_init(part_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "n"(2 * TC_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_d;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot) : "memory");
+
+    const int cx = a.C / TC_K, ch = a.has_h ? a.F / TC_K : 0;    // 32-channel chunks of x and of h_prev
+    const int per_tap = cx + ch;
+    const int nchunks = 27 * per_tap;
+    const int CF = a.C + a.F;
+    const int gsz = a.promote > 0 ? a.promote : nchunks;         // K-chunks per partial accumulation chain
+    const int ngroups = (nchunks + gsz - 1) / gsz;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        for (int it = 0; it < nchunks; ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
+            mbar_wait(empty_bar(s), phase ^ 1u);
+            const int tap = it / per_tap, kc = it - tap * per_tap;
+            const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;      // W[kx][ky][kz], SAME padding
+            const bool from_h = kc >= cx;
+            const int c0 = (from_h ? kc - cx : kc) * TC_K;
+            const int krow = tap * CF + (from_h ? a.C : 0) + c0;                        // row of the K-major weight matrix
+            const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+            mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
+            tma_load_5d(st, from_h ? &tm_hh : &tm_xh, full_bar(s), c0, z0 + dz, y0 + dy, x0 + dx, b);
+            tma_load_5d(st + TC_A_BYTES, from_h ? &tm_hl : &tm_xl, full_bar(s), c0, z0 + dz, y0 + dy, x0 + dx, b);
+            tma_load_2d(st + 2 * TC_A_BYTES, &tm_wh, full_bar(s), krow, ntile * TC_N);
+            tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tm_wl, full_bar(s), krow, ntile * TC_N);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer: D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (3xTF32) =====
+        for (int it = 0; it < nchunks; ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
+            const int grp = it / gsz, in_grp = it - grp * gsz;
+            if (in_grp == 0 && grp > 0) {                          // the previous partial must have been promoted before it is overwritten
+                mbar_wait(part_empty, (uint32_t)(grp - 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            mbar_wait(full_bar(s), phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+            const uint64_t dah = umma_desc_sw128(st), dal = umma_desc_sw128(st + TC_A_BYTES);
+            const uint64_t dbh = umma_desc_sw128(st + 2 * TC_A_BYTES), dbl = umma_desc_sw128(st + 2 * TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_K / 8; ++k) {                   // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzle atom
+                const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                umma_tf32(tmem_d, dal + adv, dbh + adv, (in_grp | k) != 0);
+                umma_tf32(tmem_d, dah + adv, dbl + adv, 1u);
+                umma_tf32(tmem_d, dah + adv, dbh + adv, 1u);
+            }
+            umma_commit(empty_bar(s));                              // frees the smem stage when these MMAs have read it
+            if (in_grp == gsz - 1 || it == nchunks - 1) umma_commit(part_full);   // partial accumulator complete
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> LSTM gates -> c, h =====
+        const int q = warp - 4;                                     // TMEM lane quadrant of this warp (warp % 4)
+        const uint32_t tpart = tmem_d + ((uint32_t)(q * 32) << 16), tmast = tpart + TC_N;
+        // promotion: master (+)= partial with round-to-nearest fp32 adds; the last group is folded into the gate epilogue
+        for (int grp = 0; grp + 1 < ngroups; ++grp) {
+            mbar_wait(part_full, (uint32_t)grp & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c16 = 0; c16 < TC_N; c16 += 16) {
+                float pv[16], mv[16];
+                tmem_ld16(tpart + c16, pv);
+                if (grp > 0) tmem_ld16(tmast + c16, mv);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (grp > 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pv[i] += mv[i];
+                }
+                tmem_st16(tmast + c16, pv);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(part_empty);
+        }
+        mbar_wait(part_full, (uint32_t)(ngroups - 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int m = q * 32 + lane;                                // accumulator row = voxel of the box, z fastest
+        const int bz = m % a.BZ, by = (m / a.BZ) % a.BY, bx = m / (a.BZ * a.BY);
+        const int x = x0 + bx, y = y0 + by, z = z0 + bz;
+        const bool ok = x < a.X && y < a.Y && z < a.Z;
+        const long long vox = (((long long)b * a.X + x) * a.Y + y) * a.Z + z;
+        const int fbase = ntile * TC_FPT;
+#pragma unroll 1
+        for (int g16 = 0; g16 < TC_FPT / 16; ++g16) {
+            float gj[16], gi[16], gf[16], go[16];
+            const uint32_t ta = tpart + (uint32_t)(g16 * 16);
+            tmem_ld16(ta + 0 * TC_FPT, gj); tmem_ld16(ta + 1 * TC_FPT, gi);      // gate order j,i,f,o  (recurrent.py:460-461)
+            tmem_ld16(ta + 2 * TC_FPT, gf); tmem_ld16(ta + 3 * TC_FPT, go);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ngroups > 1) {                                       // last partial + master
+                float mj[16], mi[16], mf[16], mo[16];
+                tmem_ld16(ta + TC_N + 0 * TC_FPT, mj); tmem_ld16(ta + TC_N + 1 * TC_FPT, mi);
+                tmem_ld16(ta + TC_N + 2 * TC_FPT, mf); tmem_ld16(ta + TC_N + 3 * TC_FPT, mo);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { gj[i] += mj[i]; gi[i] += mi[i]; gf[i] += mf[i]; go[i] += mo[i]; }
+            }
+            if (ok) {
+                const int f0 = fbase + g16 * 16;
+                float cp[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 v = a.c_prev ? ldg4(a.c_prev + vox * a.F + f0 + i) : zero4();
+                    cp[i] = v.x; cp[i + 1] = v.y; cp[i + 2] = v.z; cp[i + 3] = v.w;
+                }
+                float cn[16], hn[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int f = f0 + i;
+                    const float vj = gj[i] + a.bias[0 * a.F + f], vi = gi[i] + a.bias[1 * a.F + f];
+                    const float vf = gf[i] + a.bias[2 * a.F + f], vo = go[i] + a.bias[3 * a.F + f];
+                    const float c = cp[i] * sigmoid_acc(vf + a.forget_bias) + sigmoid_acc(vi) * tanhf(vj);   // :470-472
+                    cn[i] = c; hn[i] = tanhf(c) * sigmoid_acc(vo);                                           // :477
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    st4(a.c_out + vox * a.F + f0 + i, make_float4(cn[i], cn[i + 1], cn[i + 2], cn[i + 3]));
+                    st4(a.h_out + vox * a.F + f0 + i, make_float4(hn[i], hn[i + 1], hn[i + 2], hn[i + 3]));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(2 * TC_N) : "memory");
+    }
+}
+
+// a -> (a_hi, a_lo): a_hi keeps the top 19 bits (exactly representable in TF32), a_lo = a - a_hi (exact in fp32).
+__global__ void __launch_bounds__(256)
+tf32_split_kernel(const float4* __restrict__ in, float4* __restrict__ hi, float4* __restrict__ lo, long long n4, int relu) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = __ldg(in + i);
+    if (relu) v = relu4(v);
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    hi[i] = h; lo[i] = l;
+}
+
+// W [27*(C+F), 4F] (reference layout) -> K-major [4F, 27*(C+F)] hi and lo, rows permuted so that the four gates of a
+// 64-filter group are adjacent: row n' = (f / 64) * 256 + gate * 64 + f % 64  <-  column gate * F + f.
+__global__ void __launch_bounds__(256)
+convlstm_prepare_kernel(const float* __restrict__ W, float* __restrict__ whi, float* __restrict__ wlo, int K, int F) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // output element, k fastest
+    const long long total = (long long)K * 4 * F;
+    if (i >= total) return;
+    const int k = (int)(i % K);
+    const int np = (int)(i / K);
+    const int grp = np / TC_N, gate = (np % TC_N) / TC_FPT, fl = np % TC_FPT;
+    const float v = W[(long long)k * 4 * F + gate * F + grp * TC_FPT + fl];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    whi[i] = h; wlo[i] = v - h;
+}
+
+// ---- host: TMA descriptors through the driver entry point (no link-time dependency on libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+static bool make_act_map(CUtensorMap* tm, const float* base, int B, int X, int Y, int Z, int C, int BX, int BY, int BZ) {
+    const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)Z * C * 4, (cuuint64_t)Y * Z * C * 4, (cuuint64_t)X * Y * Z * C * 4};
+    const cuuint32_t box[5] = {(cuuint32_t)TC_K, (cuuint32_t)BZ, (cuuint32_t)BY, (cuuint32_t)BX, 1u};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool make_w_map(CUtensorMap* tm, const float* base, int K, int N) {
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_K, (cuuint32_t)TC_N};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace mvf
+
+using namespace mvf;
+
+extern "C" size_t mvf_convlstm_wsplit_bytes(int C, int F) {
+    if (C <= 0 || F <= 0) return 0;
+    return (size_t)2 * 27 * (size_t)(C + F) * 4 * F * sizeof(float);
+}
+
+extern "C" int mvf_convlstm_prepare(const float* W, int C, int F, float* wsplit, void* stream) {
+    if (!W || !wsplit) return MVF_ENULL;
+    if (C <= 0 || F <= 0) return MVF_EINVAL;
+    if (C % TC_K != 0 || F % TC_FPT != 0) return MVF_EUNSUPPORTED;
+    const int K = 27 * (C + F);
+    const long long total = (long long)K * 4 * F;
+    convlstm_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, wsplit, wsplit + total, K, F);
+    count_launch();
+    return check_launch();
+}
+
+extern "C" size_t mvf_convlstm_tc_workspace_bytes(int B, int X, int Y, int Z, int C, int F) {
+    if (B <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || F <= 0) return 0;
+    const size_t vox = (size_t)B * X * Y * Z;
+    return 2 * vox * (size_t)(C + F) * sizeof(float);                 // x_hi, x_lo, h_hi, h_lo
+}
+
+extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const float* c_prev, const float* wsplit,
+                                    const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
+                                    int flags, float* h_out, float* c_out, void* ws, size_t ws_bytes, void* stream) {
+    if (!x || !wsplit || !bias || !h_out || !c_out || !ws) return MVF_ENULL;
+    if (B <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || F <= 0) return MVF_EINVAL;
+    if ((h_prev == nullptr) != (c_prev == nullptr)) return MVF_ENULL;
+    if (h_out == h_prev || c_out == h_prev) return MVF_EINVAL;
+    if (C % TC_K != 0 || F % TC_FPT != 0) return MVF_EUNSUPPORTED;
+    if (!aligned16(x) || !aligned16(wsplit) || !aligned16(ws) || !aligned16(h_out) || !aligned16(c_out) ||
+        (h_prev && (!aligned16(h_prev) || !aligned16(c_prev)))) return MVF_EALIGN;
+    if (ws_bytes < mvf_convlstm_tc_workspace_bytes(B, X, Y, Z, C, F)) return MVF_EWORKSPACE;
+    if (!encode_tiled()) return MVF_ECUDA;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long vox = (long long)B * X * Y * Z;
+    float* xh = (float*)ws; float* xl = xh + vox * C; float* hh = xl + vox * C; float* hl = hh + vox * F;
+    {
+        const long long n4 = vox * C / 4;
+        tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)x, (float4*)xh, (float4*)xl, n4, (flags & MVF_FLAG_RELU_IN) != 0);
+        count_launch();
+    }
+    if (h_prev) {
+        const long long n4 = vox * F / 4;
+        tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)h_prev, (float4*)hh, (float4*)hl, n4, 0);
+        count_launch();
+    }
+    TcArgs a;
+    a.bias = bias; a.c_prev = c_prev; a.h_out = h_out; a.c_out = c_out;
+    a.B = B; a.X = X; a.Y = Y; a.Z = Z; a.C = C; a.F = F;
+    a.BZ = pow2ceil(Z) < TC_M ? pow2ceil(Z) : TC_M;
+    a.BY = pow2ceil(Y) < TC_M / a.BZ ? pow2ceil(Y) : TC_M / a.BZ;
+    a.BX = TC_M / (a.BZ * a.BY);
+    a.tiles_z = (Z + a.BZ - 1) / a.BZ; a.tiles_y = (Y + a.BY - 1) / a.BY; a.tiles_x = (X + a.BX - 1) / a.BX;
+    a.has_h = h_prev != nullptr; a.forget_bias = forget_bias;
+    // K-chunks (of 32) per partial accumulation chain; MVF_TC_PROMOTE overrides (0 = one long chain, for A/B measurement)
+    static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
+    a.promote = promote_env >= 0 ? promote_env : 8;
+    const int K = 27 * (C + F);
+    const float* whi = wsplit; const float* wlo = wsplit + (long long)K * 4 * F;
+    CUtensorMap tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl;
+    bool ok = make_act_map(&tm_xh, xh, B, X, Y, Z, C, a.BX, a.BY, a.BZ) && make_act_map(&tm_xl, xl, B, X, Y, Z, C, a.BX, a.BY, a.BZ) &&
+              make_act_map(&tm_hh, hh, B, X, Y, Z, F, a.BX, a.BY, a.BZ) && make_act_map(&tm_hl, hl, B, X, Y, Z, F, a.BX, a.BY, a.BZ) &&
+              make_w_map(&tm_wh, whi, K, 4 * F) && make_w_map(&tm_wl, wlo, K, 4 * F);
+    if (!ok) return MVF_ECUDA;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(convlstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
+        attr_set = true;
+    }
+    const long long mtiles = (long long)B * a.tiles_x * a.tiles_y * a.tiles_z;
+    if (mtiles > 2147483647ll || F / TC_FPT > 65535) return MVF_EUNSUPPORTED;
+    dim3 grid((unsigned)mtiles, F / TC_FPT);
+    convlstm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
+    count_launch();
+    return check_launch();
+}

@@ -184,7 +184,50 @@ def convlstm_step(x, h_prev, c_prev, W, bias, forget_bias=1.0, relu_in=False):
     return h, c
 
 
-def convlstm(grid, name, kernel=(3, 3, 3), filters=32, params=None, relu_in=False):
+def tensor_core_eligible(C_, F):
+    """The tcgen05 path of the ConvLSTM step needs 32-channel K chunks and 64-filter tiles."""
+    return C_ % 32 == 0 and F % 64 == 0
+
+
+class ConvLSTMTensorCore:
+    """ConvLSTMCell.call (mrcnn/recurrent.py:442-479) on the tensor cores: weights are split / transposed once
+    (``mvf_convlstm_prepare``), the scratch for the hi/lo halves of x and h is allocated once."""
+
+    def __init__(self, W, bias, forget_bias=1.0):
+        W = _cuda(W, "W")
+        self.bias = _cuda(bias, "bias")
+        self.F = W.shape[-1] // 4
+        self.C = W.shape[-2] - self.F
+        if tuple(W.shape) != (3, 3, 3, self.C + self.F, 4 * self.F):
+            raise ValueError("W must be [3,3,3,C+F,4F] (recurrent.py:423-426), got %s" % (tuple(W.shape),))
+        if not tensor_core_eligible(self.C, self.F):
+            raise ValueError("tensor-core ConvLSTM needs C % 32 == 0 and F % 64 == 0")
+        self.forget_bias = float(forget_bias)
+        nbytes = lib.mvf_convlstm_wsplit_bytes(self.C, self.F)
+        self.wsplit = torch.empty(nbytes // 4, dtype=torch.float32, device=W.device)
+        check(lib.mvf_convlstm_prepare(_ptr(W), self.C, self.F, _ptr(self.wsplit), _stream()), "mvf_convlstm_prepare")
+        self._ws = None
+
+    def step(self, x, h_prev, c_prev, relu_in=False):
+        x = _cuda(x, "x")
+        B, X, Y, Z, Cc = x.shape
+        if Cc != self.C:
+            raise ValueError("x has %d channels, the weights expect %d" % (Cc, self.C))
+        need = lib.mvf_convlstm_tc_workspace_bytes(B, X, Y, Z, self.C, self.F)
+        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device:
+            self._ws = torch.empty(need // 4, dtype=torch.float32, device=x.device)
+        h = torch.empty((B, X, Y, Z, self.F), dtype=torch.float32, device=x.device)
+        c = torch.empty_like(h)
+        hp = _cuda(h_prev, "h_prev") if h_prev is not None else None
+        cp = _cuda(c_prev, "c_prev") if c_prev is not None else None
+        rc = lib.mvf_convlstm_step_tc(_ptr(x), _ptr(hp), _ptr(cp), _ptr(self.wsplit), _ptr(self.bias), self.forget_bias,
+                                      B, X, Y, Z, self.C, self.F, _lib.FLAG_RELU_IN if relu_in else 0,
+                                      _ptr(h), _ptr(c), _ptr(self._ws), self._ws.numel() * 4, _stream())
+        check(rc, "mvf_convlstm_step_tc")
+        return h, c
+
+
+def convlstm(grid, name, kernel=(3, 3, 3), filters=32, params=None, relu_in=False, tensor_cores=None):
     """``convlstm(grid, name, kernel, filters)`` (model_multi.py:109-123): ConvRNN3D over the view
     axis with zero initial state, last output only.  Weights: ``weights[name] = {'W','b'}``."""
     grid = _cuda(grid, "grid")
@@ -197,6 +240,13 @@ def convlstm(grid, name, kernel=(3, 3, 3), filters=32, params=None, relu_in=Fals
         raise ValueError("initial state takes the input's channel count, so C must equal filters (recurrent.py:145-147)")
     V = grid.shape[1]
     h = c = None
+    F = p["W"].shape[-1] // 4
+    use_tc = tensor_core_eligible(grid.shape[-1], F) if tensor_cores is None else bool(tensor_cores)
+    if use_tc:                                  # tcgen05 implicit GEMM (3xTF32); same maths, ~1e-6 relative
+        cell = ConvLSTMTensorCore(p["W"], p["b"], 1.0)
+        for t in range(V):
+            h, c = cell.step(grid[:, t].contiguous(), h, c, relu_in=relu_in)
+        return h
     for t in range(V):
         h, c = convlstm_step(grid[:, t], h, c, p["W"], p["b"], 1.0, relu_in=relu_in)
     return h
