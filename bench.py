@@ -151,7 +151,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    slab = 8
+    slab = 16
     value, s_per_step, threads = cpu_reference_run(1, slab, args.steps, min(args.warmup, 1))
     sample = "1 scene of workload T restricted to an x-slab of %d/64 planes (%d voxel-samples per step) + full proj_grid" \
              % (slab, T["V"] * slab * 64 * 64)
@@ -167,6 +167,50 @@ def run_reference(args):
                     "reference graph, on all host threads"}
     print(json.dumps(line))
     return 0
+
+
+def measured_bf16_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def convlstm_line(dev):
+    """K2: one ConvLSTM step of workload c3 (C = F = 256, 64^3 voxels, recurrent state present) on the tensor cores.
+    Roofline: tensor.  `achieved` counts the TF32 MMA work actually issued (3 MMAs per product for the fp32-parity
+    split); `useful` is the conv's own 2*M*K*N.  TF32 peak = half the measured bf16 rate (same datapath, half rate)."""
+    import torch
+    import mulit_view_object_detection_b200 as m
+    X, C = 64, 256
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    W = torch.randn((3, 3, 3, 2 * C, 4 * C), device=dev, generator=g) * (2.0 / (27 * 2 * C + 4 * C)) ** 0.5
+    b = torch.randn(4 * C, device=dev, generator=g) * 0.1
+    x = torch.randn((1, X, X, X, C), device=dev, generator=g).relu_()
+    cell = m.ConvLSTMTensorCore(W, b, 1.0)
+    h, c = cell.step(x, None, None)
+    for _ in range(2):
+        cell.step(x, h, c)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 3
+    e0.record()
+    for _ in range(n):
+        h2, c2 = cell.step(x, h, c)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flop = 2.0 * X ** 3 * 27 * 2 * C * 4 * C
+    peak_bf16, src = measured_bf16_peak()
+    peak = peak_bf16 / 2.0
+    return {"workload": "c3 step: ConvLSTM 3x3x3, C=F=256, 64^3 voxels, K=13824, N=1024, fp32-parity 3xTF32 split on tcgen05",
+            "ms_per_step": ms, "useful_tflops": flop / ms / 1e9,
+            "roofline": {"bound": "tensor", "achieved": 3.0 * flop / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
+                         "frac": 3.0 * flop / ms / 1e9 / peak, "traffic": None,
+                         "peak_source": src + " / 2 for TF32", "kernel": "convlstm_tc_kernel (K2)"},
+            "checksum": float(h2.double().sum())}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -277,11 +321,15 @@ def run_b200(args):
                          "k1_ms": k1_ms, "k3_ms": k3_ms,
                          "k3_achieved_gbs": k3_bytes / (k3_ms * 1e-3) / 1e9},
         }
+        if world == 1 and not args.no_convlstm:
+            line["k2_convlstm"] = convlstm_line(dev)
         if world == 1 and not args.no_cpu_baseline:
-            v, s_per, threads = cpu_reference_run(1, 8, 1, 0)
+            n_cpu = 12
+            v, s_per, threads = cpu_reference_run(1, 16, n_cpu, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "1 scene of workload T, x-slab 8/64 of the grid (262144 voxel-samples) + full "
-                                              "proj_grid, oracle/torch_cpu.py on all host threads, %.1f s" % s_per}
+                                    "sample": "%d passes over 1 scene of workload T restricted to an x-slab of 16/64 planes (524288 "
+                                              "voxel-samples per pass) + full proj_grid, oracle/torch_cpu.py on all host threads, "
+                                              "%.1f s of CPU work" % (n_cpu, s_per * n_cpu)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -352,6 +400,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-convlstm", action="store_true", help="skip the extra K2 (ConvLSTM on tensor cores) measurement")
     ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner"],
                     help="multi-GPU sharding: scene (default, weak scaling, no collective) or one of the cooperative "
                          "strategies of dist.py on a FIXED batch of --scenes scenes (strong scaling)")
