@@ -52,7 +52,7 @@ pyramid_roi_align_kernel(const __grid_constant__ RoiParams p) {
         const float y1 = bx[0], x1 = bx[1], y2 = bx[2], x2 = bx[3];
         const int lvl = roi_level(y1, x1, y2, x2, p.image_area);
         s_lvl = lvl;
-        if (p.out_level) p.out_level[box] = lvl;
+        if (p.out_level && blockIdx.y == 0) p.out_level[box] = lvl;
         const float Hm1 = (float)(p.H[lvl - 2] - 1), Wm1 = (float)(p.W[lvl - 2] - 1);
         s_f[4] = Hm1; s_f[5] = Wm1;
         if (p.ph > 1) { s_f[0] = mul_rn(y1, Hm1); s_f[1] = div_rn(mul_rn(sub_rn(y2, y1), Hm1), (float)(p.ph - 1)); }
@@ -68,7 +68,8 @@ pyramid_roi_align_kernel(const __grid_constant__ RoiParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int C4 = p.C >> 2;
     const int nbins = p.ph * p.pw;
-    for (int bin = warp; bin < nbins; bin += nwarps) {
+    // the bins of a box are dealt round-robin to the warps of its gridDim.y CTAs
+    for (int bin = blockIdx.y * nwarps + warp; bin < nbins; bin += nwarps * gridDim.y) {
         const int iy = bin / p.pw, ix = bin % p.pw;
         const float in_y = (p.ph > 1) ? add_rn(s_f[0], mul_rn((float)iy, s_f[1])) : s_f[0];
         const float in_x = (p.pw > 1) ? add_rn(s_f[2], mul_rn((float)ix, s_f[3])) : s_f[2];
@@ -115,8 +116,12 @@ extern "C" int mvf_pyramid_roi_align(const float* boxes, const float* const maps
     p.boxes = boxes; p.out = out; p.out_level = out_level;
     p.B = B; p.R = R; p.C = C; p.ph = pool_h; p.pw = pool_w;
     p.image_area = (float)((double)image_h * (double)image_w);       // tf.cast(h*w, float32), :821
-    const int threads = (pool_h * pool_w >= 8) ? 256 : 32 * pool_h * pool_w;
-    pyramid_roi_align_kernel<<<B * R, threads, 0, (cudaStream_t)stream>>>(p);
+    const int nbins = pool_h * pool_w;
+    const int threads = (nbins >= 8) ? 256 : 32 * nbins;
+    // few boxes (the 100-box mask head): split each box's bins over several CTAs so that every SM gets work
+    int split = 1;
+    while ((long long)B * R * split < 148ll * 4 && (split + 1) * 8 <= nbins) ++split;
+    pyramid_roi_align_kernel<<<dim3(B * R, split), threads, 0, (cudaStream_t)stream>>>(p);
     count_launch();
     return check_launch();
 }
