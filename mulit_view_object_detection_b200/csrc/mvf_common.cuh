@@ -55,7 +55,6 @@ __device__ __forceinline__ bool usable_coord(float v) {
     return (fabsf(v) < 1073741824.0f);      // finite and |v| < 2^30 (NaN compares false)
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void stcs4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -81,6 +80,9 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0,
 __device__ __forceinline__ float lo2(u64 v) { return unpack2(v).x; }
 __device__ __forceinline__ float hi2(u64 v) { return unpack2(v).y; }
 __device__ __forceinline__ ulonglong2 ldg2x2(const void* p) { return __ldg(reinterpret_cast<const ulonglong2*>(p)); }
+__device__ __forceinline__ void stcs2x2(float* p, ulonglong2 v) {
+    asm volatile("st.global.cs.v2.b64 [%0], {%1, %2};" :: "l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
 // acc + w * t for four channels held as two packed pairs
 __device__ __forceinline__ ulonglong2 fma2x2(float w, ulonglong2 t, ulonglong2 a) {
     const u64 ww = dup2(w);

@@ -47,7 +47,7 @@ struct UnprojParams {
 //   phase B (lanes = float4 channel slots): walk the run.
 constexpr int RUN_WARPS = 8, RUN_TX = 4, RUN_TY = 2;
 
-template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC, int PF_MODE>
+template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC>
 __global__ void __launch_bounds__(RUN_WARPS * 32, (CPL * L <= 16) ? 2 : 1)
 unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zsplit) {
     constexpr int VPP = 32 / L;                       // views handled per phase A
@@ -133,6 +133,7 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
     const size_t view_bytes = view_stride * sizeof(float);
     const char* vbase = (const char*)feats_b + lane_off[0];
     const bool has_bn = p.bn_scale != nullptr, relu_out = (p.flags & MVF_FLAG_RELU_OUT) != 0;
+    float* const obase0 = (MODE == MVF_FUSE_NONE) ? nullptr : p.out + (((size_t)b * p.Xs + ixs) * p.Y + iy) * p.Z * C + 4 * c4base;
 
     const ulonglong2 zz = make_ulonglong2(0ull, 0ull);
     for (int tz = tz_begin; tz < tz_end; ++tz) {
@@ -216,20 +217,6 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
                                 (unsigned)(r1c * p.fw + c0c) * CB, (unsigned)(r1c * p.fw + c1c) * CB);
             }
             sO[warp][lane] = o4;
-            // L1 prefetch of the tap lines this step will load: the lanes of phase A know the addresses one
-            // whole view-loop ahead of the lanes of phase B
-            if (PF_MODE != 0 && valid) {
-                const char* tb = (const char*)(feats_b + (size_t)(v0 + sub_a) * view_stride) + (size_t)chunk * (512 * CPL);
-                const bool f0 = (PF_MODE == 2) ? (cr0 || cc0) : first, f1 = (PF_MODE == 2) ? (cr0 || cc1) : first;
-                const bool f2 = (PF_MODE == 2) ? (cr1 || cc0) : first, f3 = (PF_MODE == 2) ? (cr1 || cc1) : first;
-#pragma unroll
-                for (int ln = 0; ln < 4 * CPL; ++ln) {
-                    if (f0) prefetch_l1(tb + (o4.x & ~15u) + 128 * ln);
-                    if (f1) prefetch_l1(tb + o4.y + 128 * ln);
-                    if (f2) prefetch_l1(tb + o4.z + 128 * ln);
-                    if (f3) prefetch_l1(tb + o4.w + 128 * ln);
-                }
-            }
         }
         __syncwarp();
         // ---- phase B: lanes = float4 channel slots.  The view loop stays ROLLED (only the L z-steps are
@@ -303,20 +290,31 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
         __syncwarp();
     }
     if (MODE != MVF_FUSE_NONE) {
-        float* obase = p.out + ((((size_t)b * p.Xs + ixs) * p.Y + iy) * p.Z + z0) * C + 4 * c4base;
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            if (!FULLC && c4base + 32 * c >= C4) continue;
-            float4 bs = make_float4(1.f, 1.f, 1.f, 1.f), bh = zero4();
-            if (has_bn) { bs = ldg4(p.bn_scale + 4 * (c4base + 32 * c)); bh = ldg4(p.bn_shift + 4 * (c4base + 32 * c)); }
+        float* obase = obase0 + (size_t)z0 * C;
+        if (!has_bn && !relu_out && MODE != MVF_FUSE_MEAN) {
+            // plain sum / max: 2 streaming 128-bit stores per voxel, nothing else
 #pragma unroll
             for (int k = 0; k < L; ++k) {
                 if (z0 + k >= p.Z) break;
-                float4 r = unpack4(acc[k][c]);
-                if (MODE == MVF_FUSE_MEAN) r = mul4(p.inv_v, r);
-                if (has_bn) r = make_float4(fmaf(r.x, bs.x, bh.x), fmaf(r.y, bs.y, bh.y), fmaf(r.z, bs.z, bh.z), fmaf(r.w, bs.w, bh.w));
-                if (relu_out) r = relu4(r);
-                stcs4(obase + (size_t)k * C + 128 * c, r);
+#pragma unroll
+                for (int c = 0; c < CPL; ++c)
+                    if (FULLC || c4base + 32 * c < C4) stcs2x2(obase + (size_t)k * C + 128 * c, acc[k][c]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                if (!FULLC && c4base + 32 * c >= C4) continue;
+                float4 bs = make_float4(1.f, 1.f, 1.f, 1.f), bh = zero4();
+                if (has_bn) { bs = ldg4(p.bn_scale + 4 * (c4base + 32 * c)); bh = ldg4(p.bn_shift + 4 * (c4base + 32 * c)); }
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    if (z0 + k >= p.Z) break;
+                    float4 r = unpack4(acc[k][c]);
+                    if (MODE == MVF_FUSE_MEAN) r = mul4(p.inv_v, r);
+                    if (has_bn) r = make_float4(fmaf(r.x, bs.x, bh.x), fmaf(r.y, bs.y, bh.y), fmaf(r.z, bs.z, bh.z), fmaf(r.w, bs.w, bh.w));
+                    if (relu_out) r = relu4(r);
+                    stcs4(obase + (size_t)k * C + 128 * c, r);
+                }
             }
         }
     }
@@ -326,16 +324,10 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
 template <int CPL, int L, bool RELU_IN, bool FULLC>
 static int launch_run_mode(const UnprojParams& p, dim3 grid, int nchunk, int zsplit, cudaStream_t s) {
     switch (p.mode) {
-        case MVF_FUSE_NONE: unproject_slot_kernel<CPL, L, MVF_FUSE_NONE, RELU_IN, FULLC, 0><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
-        case MVF_FUSE_SUM: {
-            static const int pf = [] { const char* e = getenv("MVF_K1_PF"); return e ? atoi(e) : 0; }();
-            if (pf == 1) unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC, 1><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit);
-            else if (pf == 2) unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC, 2><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit);
-            else unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC, 0><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit);
-            break;
-        }
-        case MVF_FUSE_MEAN: unproject_slot_kernel<CPL, L, MVF_FUSE_MEAN, RELU_IN, FULLC, 0><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
-        case MVF_FUSE_MAX:  unproject_slot_kernel<CPL, L, MVF_FUSE_MAX, RELU_IN, FULLC, 0><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_NONE: unproject_slot_kernel<CPL, L, MVF_FUSE_NONE, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_SUM:  unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_MEAN: unproject_slot_kernel<CPL, L, MVF_FUSE_MEAN, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_MAX:  unproject_slot_kernel<CPL, L, MVF_FUSE_MAX, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
         default: return MVF_EINVAL;
     }
     count_launch();
