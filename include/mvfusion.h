@@ -101,6 +101,19 @@ int mvf_ident_fuse(const float* in, const float* weight, const float* bias,
                    const float* bn_scale, const float* bn_shift,
                    int B, int V, long long N, int C, int Cout, float* out, void* stream);
 
+/* ---- grid_reas 'ident' on the tensor cores (tcgen05, 3xTF32 split) ------------------------------
+ * Same contract as mvf_ident_fuse (model_multi.py:443-455) for C % 32 == 0 and Cout % 16 == 0
+ * (MVF_EUNSUPPORTED otherwise: use mvf_ident_fuse); the grid shape is passed as X,Y,Z (N = X*Y*Z).
+ *   mvf_ident_prepare(weight [V*C,Cout]) -> wsplit (mvf_ident_wsplit_bytes): K-major hi/lo halves, once per weight.
+ * ws: mvf_ident_tc_workspace_bytes(...) bytes of device scratch (hi/lo halves of relu(in)). */
+size_t mvf_ident_wsplit_bytes(int V, int C, int Cout);
+int mvf_ident_prepare(const float* weight, int V, int C, int Cout, float* wsplit, void* stream);
+size_t mvf_ident_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C);
+int mvf_ident_fuse_tc(const float* in, const float* wsplit, const float* bias,
+                      const float* bn_scale, const float* bn_shift,
+                      int B, int V, int X, int Y, int Z, int C, int Cout,
+                      float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- ConvLSTM cell step ----------------------------------------------------------------------
  * replaces ConvLSTMCell.call  mrcnn/recurrent.py:442-479 (driven over the view axis by
  * ConvRNN3D, recurrent.py:230-280; wrapper convlstm() model_multi.py:109-123).

@@ -44,6 +44,8 @@ struct TcArgs {
     int B, X, Y, Z, C, F;
     int BX, BY, BZ, tiles_x, tiles_y, tiles_z;
     int has_h;
+    int V, Cout;                  // ident mode: K = V*C (views concatenated on channels), Cout output channels
+    const float* bn_scale; const float* bn_shift; float* out;
     int promote;                  // K-chunks per promotion of the partial accumulator into the master (0 = never)
     float forget_bias;
 };
@@ -112,6 +114,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// IDENT = false: ConvLSTM step (27 taps, gates in the epilogue).
+// IDENT = true : grid_reas 'ident' (model_multi.py:443-455): 1x1x1 conv over the view-concatenated channels of
+//                [B,V,X,Y,Z,C] -> Cout, + bias -> BN -> ReLU; the same pipeline with one tap per view and a plain epilogue.
+template <bool IDENT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                    const __grid_constant__ CUtensorMap tm_hh, const __grid_constant__ CUtensorMap tm_hl,
@@ -152,7 +158,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
 
     const int cx = a.C / TC_K, ch = a.has_h ? a.F / TC_K : 0;    // 32-channel chunks of x and of h_prev
     const int per_tap = cx + ch;
-    const int nchunks = 27 * per_tap;
+    const int nchunks = IDENT ? a.V * cx : 27 * per_tap;
     const int CF = a.C + a.F;
     const int gsz = a.promote > 0 ? a.promote : nchunks;         // K-chunks per partial accumulation chain
     const int ngroups = (nchunks + gsz - 1) / gsz;
@@ -163,15 +169,22 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
             const int s = it % TC_STAGES;
             const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
             mbar_wait(empty_bar(s), phase ^ 1u);
-            const int tap = it / per_tap, kc = it - tap * per_tap;
-            const int dx = tap / 9 - 1, dy = (tap / 3) % 3 - 1, dz = tap % 3 - 1;      // W[kx][ky][kz], SAME padding
-            const bool from_h = kc >= cx;
-            const int c0 = (from_h ? kc - cx : kc) * TC_K;
-            const int krow = tap * CF + (from_h ? a.C : 0) + c0;                        // row of the K-major weight matrix
+            int dx = 0, dy = 0, dz = 0, c0, krow, bidx = b;
+            bool from_h = false;
+            if (IDENT) {                                                                // view v, channel chunk kc: W row v*C + c
+                const int v = it / cx, kc = it - v * cx;
+                c0 = kc * TC_K; krow = v * a.C + c0; bidx = b * a.V + v;
+            } else {
+                const int tap = it / per_tap, kc = it - tap * per_tap;
+                dx = tap / 9 - 1; dy = (tap / 3) % 3 - 1; dz = tap % 3 - 1;             // W[kx][ky][kz], SAME padding
+                from_h = kc >= cx;
+                c0 = (from_h ? kc - cx : kc) * TC_K;
+                krow = tap * CF + (from_h ? a.C : 0) + c0;                              // row of the K-major weight matrix
+            }
             const uint32_t st = smem_base + s * TC_STAGE_BYTES;
             mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
-            tma_load_5d(st, from_h ? &tm_hh : &tm_xh, full_bar(s), c0, z0 + dz, y0 + dy, x0 + dx, b);
-            tma_load_5d(st + TC_A_BYTES, from_h ? &tm_hl : &tm_xl, full_bar(s), c0, z0 + dz, y0 + dy, x0 + dx, b);
+            tma_load_5d(st, from_h ? &tm_hh : &tm_xh, full_bar(s), c0, z0 + dz, y0 + dy, x0 + dx, bidx);
+            tma_load_5d(st + TC_A_BYTES, from_h ? &tm_hl : &tm_xl, full_bar(s), c0, z0 + dz, y0 + dy, x0 + dx, bidx);
             tma_load_2d(st + 2 * TC_A_BYTES, &tm_wh, full_bar(s), krow, ntile * TC_N);
             tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tm_wl, full_bar(s), krow, ntile * TC_N);
         }
@@ -232,43 +245,71 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
         const int x = x0 + bx, y = y0 + by, z = z0 + bz;
         const bool ok = x < a.X && y < a.Y && z < a.Z;
         const long long vox = (((long long)b * a.X + x) * a.Y + y) * a.Z + z;
-        const int fbase = ntile * TC_FPT;
+        if (IDENT) {
+            // out[b, vox, co] = relu(bn(acc + bias))     (model_multi.py:449-455)
 #pragma unroll 1
-        for (int g16 = 0; g16 < TC_FPT / 16; ++g16) {
-            float gj[16], gi[16], gf[16], go[16];
-            const uint32_t ta = tpart + (uint32_t)(g16 * 16);
-            tmem_ld16(ta + 0 * TC_FPT, gj); tmem_ld16(ta + 1 * TC_FPT, gi);      // gate order j,i,f,o  (recurrent.py:460-461)
-            tmem_ld16(ta + 2 * TC_FPT, gf); tmem_ld16(ta + 3 * TC_FPT, go);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (ngroups > 1) {                                       // last partial + master
-                float mj[16], mi[16], mf[16], mo[16];
-                tmem_ld16(ta + TC_N + 0 * TC_FPT, mj); tmem_ld16(ta + TC_N + 1 * TC_FPT, mi);
-                tmem_ld16(ta + TC_N + 2 * TC_FPT, mf); tmem_ld16(ta + TC_N + 3 * TC_FPT, mo);
+            for (int c16 = 0; c16 < TC_N; c16 += 16) {
+                float v[16];
+                tmem_ld16(tpart + c16, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ngroups > 1) {
+                    float mv[16];
+                    tmem_ld16(tmast + c16, mv);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { gj[i] += mj[i]; gi[i] += mi[i]; gf[i] += mf[i]; go[i] += mo[i]; }
+                    for (int i = 0; i < 16; ++i) v[i] += mv[i];
+                }
+                const int co0 = ntile * TC_N + c16;
+                if (ok && co0 < a.Cout) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float y = v[i] + a.bias[co0 + i];
+                        if (a.bn_scale) y = fmaf(y, a.bn_scale[co0 + i], a.bn_shift[co0 + i]);
+                        v[i] = fmaxf(y, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) st4(a.out + vox * a.Cout + co0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                }
             }
-            if (ok) {
-                const int f0 = fbase + g16 * 16;
-                float cp[16];
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 v = a.c_prev ? ldg4(a.c_prev + vox * a.F + f0 + i) : zero4();
-                    cp[i] = v.x; cp[i + 1] = v.y; cp[i + 2] = v.z; cp[i + 3] = v.w;
+        } else {
+        const int fbase = ntile * TC_FPT;
+    #pragma unroll 1
+            for (int g16 = 0; g16 < TC_FPT / 16; ++g16) {
+                float gj[16], gi[16], gf[16], go[16];
+                const uint32_t ta = tpart + (uint32_t)(g16 * 16);
+                tmem_ld16(ta + 0 * TC_FPT, gj); tmem_ld16(ta + 1 * TC_FPT, gi);      // gate order j,i,f,o  (recurrent.py:460-461)
+                tmem_ld16(ta + 2 * TC_FPT, gf); tmem_ld16(ta + 3 * TC_FPT, go);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ngroups > 1) {                                       // last partial + master
+                    float mj[16], mi[16], mf[16], mo[16];
+                    tmem_ld16(ta + TC_N + 0 * TC_FPT, mj); tmem_ld16(ta + TC_N + 1 * TC_FPT, mi);
+                    tmem_ld16(ta + TC_N + 2 * TC_FPT, mf); tmem_ld16(ta + TC_N + 3 * TC_FPT, mo);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+                    for (int i = 0; i < 16; ++i) { gj[i] += mj[i]; gi[i] += mi[i]; gf[i] += mf[i]; go[i] += mo[i]; }
                 }
-                float cn[16], hn[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int f = f0 + i;
-                    const float vj = gj[i] + a.bias[0 * a.F + f], vi = gi[i] + a.bias[1 * a.F + f];
-                    const float vf = gf[i] + a.bias[2 * a.F + f], vo = go[i] + a.bias[3 * a.F + f];
-                    const float c = cp[i] * sigmoid_acc(vf + a.forget_bias) + sigmoid_acc(vi) * tanhf(vj);   // :470-472
-                    cn[i] = c; hn[i] = tanhf(c) * sigmoid_acc(vo);                                           // :477
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    st4(a.c_out + vox * a.F + f0 + i, make_float4(cn[i], cn[i + 1], cn[i + 2], cn[i + 3]));
-                    st4(a.h_out + vox * a.F + f0 + i, make_float4(hn[i], hn[i + 1], hn[i + 2], hn[i + 3]));
+                if (ok) {
+                    const int f0 = fbase + g16 * 16;
+                    float cp[16];
+    #pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 v = a.c_prev ? ldg4(a.c_prev + vox * a.F + f0 + i) : zero4();
+                        cp[i] = v.x; cp[i + 1] = v.y; cp[i + 2] = v.z; cp[i + 3] = v.w;
+                    }
+                    float cn[16], hn[16];
+    #pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int f = f0 + i;
+                        const float vj = gj[i] + a.bias[0 * a.F + f], vi = gi[i] + a.bias[1 * a.F + f];
+                        const float vf = gf[i] + a.bias[2 * a.F + f], vo = go[i] + a.bias[3 * a.F + f];
+                        const float c = cp[i] * sigmoid_acc(vf + a.forget_bias) + sigmoid_acc(vi) * tanhf(vj);   // :470-472
+                        cn[i] = c; hn[i] = tanhf(c) * sigmoid_acc(vo);                                           // :477
+                    }
+    #pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        st4(a.c_out + vox * a.F + f0 + i, make_float4(cn[i], cn[i + 1], cn[i + 2], cn[i + 3]));
+                        st4(a.h_out + vox * a.F + f0 + i, make_float4(hn[i], hn[i + 1], hn[i + 2], hn[i + 3]));
+                    }
                 }
             }
         }
@@ -307,6 +348,17 @@ convlstm_prepare_kernel(const float* __restrict__ W, float* __restrict__ whi, fl
     const int np = (int)(i / K);
     const int grp = np / TC_N, gate = (np % TC_N) / TC_FPT, fl = np % TC_FPT;
     const float v = W[(long long)k * 4 * F + gate * F + grp * TC_FPT + fl];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    whi[i] = h; wlo[i] = v - h;
+}
+
+// W [K, N] (reference layout, N fastest) -> K-major [N, K] hi and lo halves (no row permutation).
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ W, float* __restrict__ whi, float* __restrict__ wlo, int K, int N) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // output element, k fastest
+    if (i >= (long long)K * N) return;
+    const int k = (int)(i % K), n = (int)(i / K);
+    const float v = W[(long long)k * N + n];
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     whi[i] = h; wlo[i] = v - h;
 }
@@ -401,6 +453,7 @@ extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const f
     a.BX = TC_M / (a.BZ * a.BY);
     a.tiles_z = (Z + a.BZ - 1) / a.BZ; a.tiles_y = (Y + a.BY - 1) / a.BY; a.tiles_x = (X + a.BX - 1) / a.BX;
     a.has_h = h_prev != nullptr; a.forget_bias = forget_bias;
+    a.V = 1; a.Cout = 0; a.bn_scale = nullptr; a.bn_shift = nullptr; a.out = nullptr;
     // K-chunks (of 32) per partial accumulation chain; MVF_TC_PROMOTE overrides (0 = one long chain, for A/B measurement)
     static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
     a.promote = promote_env >= 0 ? promote_env : 8;
@@ -413,13 +466,81 @@ extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const f
     if (!ok) return MVF_ECUDA;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(convlstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
+        if (cudaFuncSetAttribute(convlstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
         attr_set = true;
     }
     const long long mtiles = (long long)B * a.tiles_x * a.tiles_y * a.tiles_z;
     if (mtiles > 2147483647ll || F / TC_FPT > 65535) return MVF_EUNSUPPORTED;
     dim3 grid((unsigned)mtiles, F / TC_FPT);
-    convlstm_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
+    convlstm_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
+    count_launch();
+    return check_launch();
+}
+
+// ---- grid_reas 'ident' on the tensor cores (model_multi.py:443-455) ---------------------------------------------
+extern "C" size_t mvf_ident_wsplit_bytes(int V, int C, int Cout) {
+    if (V <= 0 || C <= 0 || Cout <= 0) return 0;
+    return (size_t)2 * V * C * Cout * sizeof(float);
+}
+
+extern "C" int mvf_ident_prepare(const float* weight, int V, int C, int Cout, float* wsplit, void* stream) {
+    if (!weight || !wsplit) return MVF_ENULL;
+    if (V <= 0 || C <= 0 || Cout <= 0) return MVF_EINVAL;
+    if (C % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
+    const long long total = (long long)V * C * Cout;
+    transpose_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(weight, wsplit, wsplit + total, V * C, Cout);
+    count_launch();
+    return check_launch();
+}
+
+extern "C" size_t mvf_ident_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C) {
+    if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0) return 0;
+    return (size_t)2 * B * V * X * Y * Z * C * sizeof(float);          // hi and lo halves of relu(in)
+}
+
+extern "C" int mvf_ident_fuse_tc(const float* in, const float* wsplit, const float* bias,
+                                 const float* bn_scale, const float* bn_shift,
+                                 int B, int V, int X, int Y, int Z, int C, int Cout,
+                                 float* out, void* ws, size_t ws_bytes, void* stream) {
+    if (!in || !wsplit || !bias || !out || !ws) return MVF_ENULL;
+    if ((bn_scale == nullptr) != (bn_shift == nullptr)) return MVF_ENULL;
+    if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || Cout <= 0) return MVF_EINVAL;
+    if (C % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
+    if (!aligned16(in) || !aligned16(wsplit) || !aligned16(ws) || !aligned16(out)) return MVF_EALIGN;
+    if (ws_bytes < mvf_ident_tc_workspace_bytes(B, V, X, Y, Z, C)) return MVF_EWORKSPACE;
+    if (!encode_tiled()) return MVF_ECUDA;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n = (long long)B * V * X * Y * Z * C;
+    float* xh = (float*)ws; float* xl = xh + n;
+    tf32_split_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)xh, (float4*)xl, n / 4, 1);   // ReLU of :448
+    count_launch();
+    TcArgs a;
+    a.bias = bias; a.c_prev = nullptr; a.h_out = nullptr; a.c_out = nullptr;
+    a.B = B; a.X = X; a.Y = Y; a.Z = Z; a.C = C; a.F = 0;
+    a.BZ = pow2ceil(Z) < TC_M ? pow2ceil(Z) : TC_M;
+    a.BY = pow2ceil(Y) < TC_M / a.BZ ? pow2ceil(Y) : TC_M / a.BZ;
+    a.BX = TC_M / (a.BZ * a.BY);
+    a.tiles_z = (Z + a.BZ - 1) / a.BZ; a.tiles_y = (Y + a.BY - 1) / a.BY; a.tiles_x = (X + a.BX - 1) / a.BX;
+    a.has_h = 0; a.forget_bias = 0.f;
+    a.V = V; a.Cout = Cout; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.out = out;
+    static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
+    a.promote = promote_env >= 0 ? promote_env : 8;
+    const int K = V * C;
+    const float* whi = wsplit; const float* wlo = wsplit + (long long)K * Cout;
+    CUtensorMap tm_xh, tm_xl, tm_wh, tm_wl;
+    bool ok = make_act_map(&tm_xh, xh, B * V, X, Y, Z, C, a.BX, a.BY, a.BZ) && make_act_map(&tm_xl, xl, B * V, X, Y, Z, C, a.BX, a.BY, a.BZ) &&
+              make_w_map(&tm_wh, whi, K, Cout) && make_w_map(&tm_wl, wlo, K, Cout);
+    if (!ok) return MVF_ECUDA;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(convlstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
+        attr_set = true;
+    }
+    const long long mtiles = (long long)B * a.tiles_x * a.tiles_y * a.tiles_z;
+    const int ntiles = (Cout + TC_N - 1) / TC_N;
+    if (mtiles > 2147483647ll || ntiles > 65535) return MVF_EUNSUPPORTED;
+    dim3 grid((unsigned)mtiles, ntiles);
+    convlstm_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_xh, tm_xl, tm_wh, tm_wl, a);
     count_launch();
     return check_launch();
 }

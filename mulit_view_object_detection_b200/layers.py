@@ -227,6 +227,44 @@ class ConvLSTMTensorCore:
         return h, c
 
 
+_cells = {}      # one prepared cell per layer name, like the reference's `reused_lay` (model_multi.py:112-117)
+
+
+def _cached_cell(name, p):
+    key = (name, p["W"].data_ptr(), p["W"]._version, p["b"].data_ptr(), p["b"]._version)
+    hit = _cells.get(name)
+    if hit is None or hit[0] != key:
+        hit = (key, ConvLSTMTensorCore(p["W"], p["b"], 1.0))
+        _cells[name] = hit
+    return hit[1]
+
+
+class IdentTensorCore:
+    """grid_reas 'ident' (model_multi.py:443-455) on the tensor cores: the 1x1x1 conv over the view-concatenated
+    channels is a [N, V*C] x [V*C, Cout] GEMM; weights are split / transposed once (``mvf_ident_prepare``)."""
+
+    def __init__(self, weight, V, C_, Cout):
+        weight = _cuda(weight, "weight").reshape(V * C_, Cout)
+        self.V, self.C, self.Cout = V, C_, Cout
+        self.wsplit = torch.empty(lib.mvf_ident_wsplit_bytes(V, C_, Cout) // 4, dtype=torch.float32, device=weight.device)
+        check(lib.mvf_ident_prepare(_ptr(weight), V, C_, Cout, _ptr(self.wsplit), _stream()), "mvf_ident_prepare")
+        self._ws = None
+
+    def __call__(self, x, bias, scale, shift):
+        B, V, X, Y, Z, Cc = x.shape
+        need = lib.mvf_ident_tc_workspace_bytes(B, V, X, Y, Z, Cc)
+        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device:
+            self._ws = torch.empty(need // 4, dtype=torch.float32, device=x.device)
+        out = torch.empty((B, X, Y, Z, self.Cout), dtype=torch.float32, device=x.device)
+        rc = lib.mvf_ident_fuse_tc(_ptr(x), _ptr(self.wsplit), _ptr(bias), _ptr(scale), _ptr(shift), B, V, X, Y, Z, Cc,
+                                   self.Cout, _ptr(out), _ptr(self._ws), self._ws.numel() * 4, _stream())
+        check(rc, "mvf_ident_fuse_tc")
+        return out
+
+
+_idents = {}
+
+
 def convlstm(grid, name, kernel=(3, 3, 3), filters=32, params=None, relu_in=False, tensor_cores=None):
     """``convlstm(grid, name, kernel, filters)`` (model_multi.py:109-123): ConvRNN3D over the view
     axis with zero initial state, last output only.  Weights: ``weights[name] = {'W','b'}``."""
@@ -243,7 +281,7 @@ def convlstm(grid, name, kernel=(3, 3, 3), filters=32, params=None, relu_in=Fals
     F = p["W"].shape[-1] // 4
     use_tc = tensor_core_eligible(grid.shape[-1], F) if tensor_cores is None else bool(tensor_cores)
     if use_tc:                                  # tcgen05 implicit GEMM (3xTF32); same maths, ~1e-6 relative
-        cell = ConvLSTMTensorCore(p["W"], p["b"], 1.0)
+        cell = _cached_cell(name, p)
         for t in range(V):
             h, c = cell.step(grid[:, t].contiguous(), h, c, relu_in=relu_in)
         return h
@@ -252,7 +290,7 @@ def convlstm(grid, name, kernel=(3, 3, 3), filters=32, params=None, relu_in=Fals
     return h
 
 
-def grid_reas(inputs, scope, config, kernel=(3, 3, 3), params=None):
+def grid_reas(inputs, scope, config, kernel=(3, 3, 3), params=None, tensor_cores=None):
     """``grid_reas(inputs, scope, config)`` (model_multi.py:394-463) on a materialised
     [B,V,X,Y,Z,C] tensor; modes add | mean | max | ident | lstm3d."""
     x = _cuda(inputs, "inputs")
@@ -270,6 +308,14 @@ def grid_reas(inputs, scope, config, kernel=(3, 3, 3), params=None):
         Cout = Wt.shape[-1]
         bias = _cuda(p["bias"], "bias")
         scale, shift = _bn_affine(p.get("bn", _default_bn(Cout)), Cout, x.device)
+        use_tc = (Cc % 32 == 0 and Cout % 16 == 0) if tensor_cores is None else bool(tensor_cores)
+        if use_tc:                              # tcgen05 GEMM (3xTF32)
+            key = (Wt.data_ptr(), Wt._version, V, Cc, Cout)
+            hit = _idents.get(scope)
+            if hit is None or hit[0] != key:
+                hit = (key, IdentTensorCore(Wt, V, Cc, Cout))
+                _idents[scope] = hit
+            return hit[1](x, bias, scale, shift)
         out = torch.empty((B, X, Y, Z, Cout), dtype=torch.float32, device=x.device)
         rc = lib.mvf_ident_fuse(_ptr(x), _ptr(Wt.reshape(V * Cc, Cout)), _ptr(bias), _ptr(scale), _ptr(shift),
                                 B, V, X * Y * Z, Cc, Cout, _ptr(out), _stream())

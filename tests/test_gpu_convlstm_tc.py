@@ -74,3 +74,24 @@ def test_grid_reas_lstm3d_uses_tensor_cores():
     o = oracle.grid_reas(grids, "grid_reas_P4", cfg, {"W": W, "b": b, "bn": bn})
     close(out.cpu().numpy(), o, rtol=1e-5, atol=5e-6)
     assert m.launch_count() - n0 >= 1 + V            # prepare + one tensor-core step per view (plus the hi/lo split passes)
+
+
+@pytest.mark.parametrize("B,V,X,Y,Z,C,Cout", [(1, 3, 4, 4, 8, 32, 64), (2, 2, 3, 5, 6, 64, 48), (1, 4, 2, 2, 32, 64, 256),
+                                              (1, 2, 4, 4, 8, 32, 320)])
+def test_ident_tc_matches_oracle(B, V, X, Y, Z, C, Cout):
+    """grid_reas('ident') (model_multi.py:443-455) on the tensor cores vs the oracle and vs the CUDA-core kernel."""
+    m = _m()
+    from helpers import small_cfg
+    rng = np.random.default_rng(V * 100 + Cout)
+    cfg = small_cfg(GRID_REAS="ident", NUM_VIEWS=V, nvox=X, nvox_z=Z)
+    grids = rng.standard_normal((B, V, X, Y, Z, C)).astype(np.float32)
+    W = (rng.standard_normal((V * C, Cout)) * 0.1).astype(np.float32)
+    b = rng.normal(0, 0.1, Cout).astype(np.float32)
+    bn = (np.full(Cout, 0.9, np.float32), np.full(Cout, 0.1, np.float32), np.zeros(Cout, np.float32), np.ones(Cout, np.float32))
+    dg, dW, db = to_dev(grids, W, b)
+    params = {"weight": dW, "bias": db, "bn": bn}
+    out = m.grid_reas(dg, "ident_tc_%d_%d" % (V, Cout), cfg, params=params, tensor_cores=True)
+    o = oracle.grid_reas(grids, "grid_reas_P4", cfg, {"weight": W, "bias": b, "bn": bn})
+    close(out.cpu().numpy(), o, rtol=1e-5, atol=5e-6)
+    ref = m.grid_reas(dg, "ident_fp32", cfg, params=params, tensor_cores=False)
+    close(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=5e-6)
