@@ -355,15 +355,25 @@ def run_cooperative(args):
     cfg = make_config(B)
     feats, Rcam, Kmat = syn.make_scene(cfg, B, T["V"], T["fh"], T["fw"], T["C"], seed=1000)   # same scenes on every rank
     d = [torch.from_numpy(a).to(dev) for a in (feats, Rcam, Kmat)]
-    fn = {"view_allreduce": mvd.view_shard_allreduce, "view_reduce_scatter": mvd.view_shard_reduce_scatter,
-          "slab_owner": mvd.slab_owner}[args.strategy]
+    if args.strategy == "lstm_slab":
+        # config c3: recurrent fusion (ConvLSTM over the 8 views, C = F = 256) with the grid split into x-slabs,
+        # one halo exchange of h per step; the tensor cores do 59 TFLOP of useful work per scene
+        g = torch.Generator(device=dev)
+        g.manual_seed(0)
+        Cc = T["C"]
+        params = {"W": torch.randn((3, 3, 3, 2 * Cc, 4 * Cc), device=dev, generator=g) * (2.0 / (27 * 2 * Cc + 4 * Cc)) ** 0.5,
+                  "b": torch.randn(4 * Cc, device=dev, generator=g) * 0.1}
+        fn = lambda f, R, K, cfg_, P, mode: mvd.lstm_slab(f, R, K, cfg_, params, proj_size=P)
+    else:
+        fn = {"view_allreduce": mvd.view_shard_allreduce, "view_reduce_scatter": mvd.view_shard_reduce_scatter,
+              "slab_owner": mvd.slab_owner}[args.strategy]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) if args.strategy != "lstm_slab" else 1):
         fn(*d, cfg, T["P"], mode="sum")
     barrier()
     stream = torch.cuda.current_stream()
@@ -383,10 +393,17 @@ def run_cooperative(args):
         value = B * T["V"] * T["nvox"] ** 3 * args.steps / (total_ms * 1e-3)
         cfgd = workload_config(args, world)
         cfgd["sharding"] = args.strategy
+        if args.strategy == "lstm_slab":
+            cfgd["workload"] = "c3: %d-view scene, 64^3 grid, recurrent voxel fusion (ConvLSTM 3x3x3, C=F=256, 3xTF32 on tcgen05), " \
+                               "x-slabs + 1-voxel halo of h exchanged per step, then proj_grid" % T["V"]
+            flop = 2.0 * T["nvox"] ** 3 * 27 * 2 * T["C"] * 4 * T["C"] * T["V"] * B
+            extra = {"useful_tflops": flop * args.steps / (total_ms * 1e-3) / 1e12}
+        else:
+            extra = {}
         print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                           "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
-                          "gpu_launches": int(launches), "checksum": float(rays.double().sum())}))
+                          "gpu_launches": int(launches), "checksum": float(rays.double().sum()), **extra}))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -401,7 +418,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-convlstm", action="store_true", help="skip the extra K2 (ConvLSTM on tensor cores) measurement")
-    ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner"],
+    ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner", "lstm_slab"],
                     help="multi-GPU sharding: scene (default, weak scaling, no collective) or one of the cooperative "
                          "strategies of dist.py on a FIXED batch of --scenes scenes (strong scaling)")
     args = ap.parse_args()

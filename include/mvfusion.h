@@ -138,6 +138,16 @@ int mvf_convlstm_step_tc(const float* x, const float* h_prev, const float* c_pre
                          const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
                          int flags, float* h_out, float* c_out, void* ws, size_t ws_bytes, void* stream);
 
+/* Slab form for the multi-GPU recurrence (x-slabs + 1-voxel halo of x and h): X is the slab's OWN extent;
+ * x, h_prev and h_out carry halo_lo + X + halo_hi planes in x (halo_* in {0,1}: 1 where a neighbouring slab exists,
+ * its plane filled by the caller's halo exchange; 0 at the grid border, where SAME padding applies); c_prev and
+ * c_out carry X planes.  h_out is written at planes [halo_lo, halo_lo + X); its halo planes are left untouched.
+ * ws: mvf_convlstm_tc_workspace_bytes(B, halo_lo + X + halo_hi, Y, Z, C, F). */
+int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, const float* c_prev, const float* wsplit,
+                              const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
+                              int halo_lo, int halo_hi, int flags, float* h_out, float* c_out,
+                              void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K3: proj_grid ---------------------------------------------------------------------------
  * replaces proj_grid([grid,Rcam,Kmat], config, proj_size)  model_multi.py:231-322 + nearest3 :357-369
  * grid [B,Xs,Y,Z,C] (slab [x_begin, x_begin+x_count) of the full grid; x_count==0 -> whole)

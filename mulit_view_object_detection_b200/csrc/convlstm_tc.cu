@@ -44,6 +44,7 @@ struct TcArgs {
     int B, X, Y, Z, C, F;
     int BX, BY, BZ, tiles_x, tiles_y, tiles_z;
     int has_h;
+    int halo_lo, halo_hi;         // slab mode: x and h_prev / h_out carry halo_lo + X + halo_hi planes in x, c_prev / c_out carry X
     int V, Cout;                  // ident mode: K = V*C (views concatenated on channels), Cout output channels
     const float* bn_scale; const float* bn_shift; float* out;
     int promote;                  // K-chunks per promotion of the partial accumulator into the master (0 = never)
@@ -183,8 +184,9 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
             }
             const uint32_t st = smem_base + s * TC_STAGE_BYTES;
             mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
-            tma_load_5d(st, from_h ? &tm_hh : &tm_xh, full_bar(s), c0, z0 + dz, y0 + dy, x0 + dx, bidx);
-            tma_load_5d(st + TC_A_BYTES, from_h ? &tm_hl : &tm_xl, full_bar(s), c0, z0 + dz, y0 + dy, x0 + dx, bidx);
+            const int xin = x0 + dx + a.halo_lo;                      // halo planes hold the neighbour slab's data; past them the TMA
+            tma_load_5d(st, from_h ? &tm_hh : &tm_xh, full_bar(s), c0, z0 + dz, y0 + dy, xin, bidx);      // zero fill is the grid border
+            tma_load_5d(st + TC_A_BYTES, from_h ? &tm_hl : &tm_xl, full_bar(s), c0, z0 + dz, y0 + dy, xin, bidx);
             tma_load_2d(st + 2 * TC_A_BYTES, &tm_wh, full_bar(s), krow, ntile * TC_N);
             tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tm_wl, full_bar(s), krow, ntile * TC_N);
         }
@@ -245,6 +247,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
         const int x = x0 + bx, y = y0 + by, z = z0 + bz;
         const bool ok = x < a.X && y < a.Y && z < a.Z;
         const long long vox = (((long long)b * a.X + x) * a.Y + y) * a.Z + z;
+        const long long voxh = (((long long)b * (a.X + a.halo_lo + a.halo_hi) + x + a.halo_lo) * a.Y + y) * a.Z + z;   // h_out keeps the halo planes
         if (IDENT) {
             // out[b, vox, co] = relu(bn(acc + bias))     (model_multi.py:449-455)
 #pragma unroll 1
@@ -308,7 +311,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
     #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
                         st4(a.c_out + vox * a.F + f0 + i, make_float4(cn[i], cn[i + 1], cn[i + 2], cn[i + 3]));
-                        st4(a.h_out + vox * a.F + f0 + i, make_float4(hn[i], hn[i + 1], hn[i + 2], hn[i + 3]));
+                        st4(a.h_out + voxh * a.F + f0 + i, make_float4(hn[i], hn[i + 1], hn[i + 2], hn[i + 3]));
                     }
                 }
             }
@@ -420,20 +423,23 @@ extern "C" size_t mvf_convlstm_tc_workspace_bytes(int B, int X, int Y, int Z, in
     return 2 * vox * (size_t)(C + F) * sizeof(float);                 // x_hi, x_lo, h_hi, h_lo
 }
 
-extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const float* c_prev, const float* wsplit,
-                                    const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
-                                    int flags, float* h_out, float* c_out, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, const float* c_prev, const float* wsplit,
+                                         const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
+                                         int halo_lo, int halo_hi, int flags, float* h_out, float* c_out,
+                                         void* ws, size_t ws_bytes, void* stream) {
     if (!x || !wsplit || !bias || !h_out || !c_out || !ws) return MVF_ENULL;
     if (B <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || F <= 0) return MVF_EINVAL;
+    if (halo_lo < 0 || halo_lo > 1 || halo_hi < 0 || halo_hi > 1) return MVF_EINVAL;
+    const int Xin = X + halo_lo + halo_hi;
     if ((h_prev == nullptr) != (c_prev == nullptr)) return MVF_ENULL;
     if (h_out == h_prev || c_out == h_prev) return MVF_EINVAL;
     if (C % TC_K != 0 || F % TC_FPT != 0) return MVF_EUNSUPPORTED;
     if (!aligned16(x) || !aligned16(wsplit) || !aligned16(ws) || !aligned16(h_out) || !aligned16(c_out) ||
         (h_prev && (!aligned16(h_prev) || !aligned16(c_prev)))) return MVF_EALIGN;
-    if (ws_bytes < mvf_convlstm_tc_workspace_bytes(B, X, Y, Z, C, F)) return MVF_EWORKSPACE;
+    if (ws_bytes < mvf_convlstm_tc_workspace_bytes(B, Xin, Y, Z, C, F)) return MVF_EWORKSPACE;
     if (!encode_tiled()) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
-    const long long vox = (long long)B * X * Y * Z;
+    const long long vox = (long long)B * Xin * Y * Z;
     float* xh = (float*)ws; float* xl = xh + vox * C; float* hh = xl + vox * C; float* hl = hh + vox * F;
     {
         const long long n4 = vox * C / 4;
@@ -453,6 +459,7 @@ extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const f
     a.BX = TC_M / (a.BZ * a.BY);
     a.tiles_z = (Z + a.BZ - 1) / a.BZ; a.tiles_y = (Y + a.BY - 1) / a.BY; a.tiles_x = (X + a.BX - 1) / a.BX;
     a.has_h = h_prev != nullptr; a.forget_bias = forget_bias;
+    a.halo_lo = halo_lo; a.halo_hi = halo_hi;
     a.V = 1; a.Cout = 0; a.bn_scale = nullptr; a.bn_shift = nullptr; a.out = nullptr;
     // K-chunks (of 32) per partial accumulation chain; MVF_TC_PROMOTE overrides (0 = one long chain, for A/B measurement)
     static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
@@ -460,8 +467,8 @@ extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const f
     const int K = 27 * (C + F);
     const float* whi = wsplit; const float* wlo = wsplit + (long long)K * 4 * F;
     CUtensorMap tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl;
-    bool ok = make_act_map(&tm_xh, xh, B, X, Y, Z, C, a.BX, a.BY, a.BZ) && make_act_map(&tm_xl, xl, B, X, Y, Z, C, a.BX, a.BY, a.BZ) &&
-              make_act_map(&tm_hh, hh, B, X, Y, Z, F, a.BX, a.BY, a.BZ) && make_act_map(&tm_hl, hl, B, X, Y, Z, F, a.BX, a.BY, a.BZ) &&
+    bool ok = make_act_map(&tm_xh, xh, B, Xin, Y, Z, C, a.BX, a.BY, a.BZ) && make_act_map(&tm_xl, xl, B, Xin, Y, Z, C, a.BX, a.BY, a.BZ) &&
+              make_act_map(&tm_hh, hh, B, Xin, Y, Z, F, a.BX, a.BY, a.BZ) && make_act_map(&tm_hl, hl, B, Xin, Y, Z, F, a.BX, a.BY, a.BZ) &&
               make_w_map(&tm_wh, whi, K, 4 * F) && make_w_map(&tm_wl, wlo, K, 4 * F);
     if (!ok) return MVF_ECUDA;
     static bool attr_set = false;
@@ -475,6 +482,13 @@ extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const f
     convlstm_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
     count_launch();
     return check_launch();
+}
+
+extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const float* c_prev, const float* wsplit,
+                                    const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
+                                    int flags, float* h_out, float* c_out, void* ws, size_t ws_bytes, void* stream) {
+    return mvf_convlstm_step_tc_slab(x, h_prev, c_prev, wsplit, bias, forget_bias, B, X, Y, Z, C, F, 0, 0, flags, h_out, c_out,
+                                     ws, ws_bytes, stream);
 }
 
 // ---- grid_reas 'ident' on the tensor cores (model_multi.py:443-455) ---------------------------------------------
@@ -521,7 +535,7 @@ extern "C" int mvf_ident_fuse_tc(const float* in, const float* wsplit, const flo
     a.BY = pow2ceil(Y) < TC_M / a.BZ ? pow2ceil(Y) : TC_M / a.BZ;
     a.BX = TC_M / (a.BZ * a.BY);
     a.tiles_z = (Z + a.BZ - 1) / a.BZ; a.tiles_y = (Y + a.BY - 1) / a.BY; a.tiles_x = (X + a.BX - 1) / a.BX;
-    a.has_h = 0; a.forget_bias = 0.f;
+    a.has_h = 0; a.forget_bias = 0.f; a.halo_lo = 0; a.halo_hi = 0;
     a.V = V; a.Cout = Cout; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.out = out;
     static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
     a.promote = promote_env >= 0 ? promote_env : 8;

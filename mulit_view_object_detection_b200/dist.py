@@ -3,7 +3,7 @@ NVLink 5 / NVSwitch on the B200 box, gloo in the CPU tests) for the plumbing.
 
 The reference has no multi-GPU path at all (its ``GPU_COUNT > 1`` branch imports a module that
 does not exist, mrcnn/model_multi.py:2557-2559), so this layer is new; SURVEY.md section 8(e) is its spec.
-Four strategies, all producing the same ray slices ``proj_grid(grid_reas(unproj_feat(...)))``:
+Five strategies, all producing the same ray slices ``proj_grid(grid_reas(unproj_feat(...)))``:
 
 * ``scene_shard``          scenes are independent: rank r takes scenes r::world, no collective.
 * ``view_shard_allreduce`` rank r unprojects its views into a full-size partial grid, one
@@ -11,6 +11,10 @@ Four strategies, all producing the same ray slices ``proj_grid(grid_reas(unproj_
 * ``view_shard_reduce_scatter``  partial grids are reduce-scattered into x-slabs, each rank
                            projects from its slab only (a ray sample comes from exactly one
                            slab, the others contribute 0) and the small ray tensor is all-reduced.
+* ``lstm_slab``            recurrent fusion (GRID_REAS='lstm3d') cannot shard views (the ConvLSTM is sequential in
+                           the view axis): ranks own x-slabs, unproject view t for their slab + 1-voxel halo, run the
+                           ConvLSTM step slab-locally and exchange the two boundary planes of ``h`` with their
+                           neighbours after every step (isend/irecv), then project slab-locally.
 * ``slab_owner``           features are tiny (13 MB for 8 views): every rank holds all views,
                            unprojects ALL of them for its own x-slab (no grid exchange at all),
                            projects locally, all-reduces the ray tensor.
@@ -46,6 +50,16 @@ class CudaOps:
                                       layers._ptr(scale), layers._ptr(shift), layers._ptr(out), layers._stream())
         _lib.check(rc, "mvf_view_reduce")
         return out
+
+
+    def convlstm_cell(self, W, bias):
+        from . import layers
+        return layers.ConvLSTMTensorCore(W, bias, 1.0)
+
+    def affine_relu(self, h, bn):
+        from . import layers
+        scale, shift = layers._bn_affine(bn if bn is not None else layers._default_bn(h.shape[-1]), h.shape[-1], h.device)
+        return layers._affine_relu(h.contiguous(), scale, shift)
 
 
 def world(group=None):
@@ -179,3 +193,64 @@ def scene_shard(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, op
     for r in range(ws):
         out[r::ws] = parts[r]
     return out, mine
+
+
+def _peer(group, r):
+    return dist.get_global_rank(group, r) if group is not None else r
+
+
+def exchange_halo(h, lo, hi, group=None):
+    """``h`` [B, lo+Xs+hi, Y, Z, F] with valid interior planes: the first interior plane goes to rank-1 (it becomes
+    that rank's high halo plane), the last interior plane to rank+1 (its low halo plane); the received planes are
+    written into this rank's halo planes.  2 x Y*Z*F*4 bytes per neighbour (4 MB at 64^2 x 256)."""
+    rank, ws = world(group)
+    if ws == 1 or not (lo or hi):
+        return h
+    Xin = h.shape[1]
+    ops, recv_lo, recv_hi = [], None, None
+    if lo:
+        send = h[:, lo].contiguous()
+        recv_lo = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send, _peer(group, rank - 1), group),
+                dist.P2POp(dist.irecv, recv_lo, _peer(group, rank - 1), group)]
+    if hi:
+        send = h[:, Xin - 1 - hi].contiguous()
+        recv_hi = torch.empty_like(send)
+        ops += [dist.P2POp(dist.isend, send, _peer(group, rank + 1), group),
+                dist.P2POp(dist.irecv, recv_hi, _peer(group, rank + 1), group)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    if lo:
+        h[:, 0].copy_(recv_lo)
+    if hi:
+        h[:, Xin - 1].copy_(recv_hi)
+    return h
+
+
+def lstm_slab(feats, Rcam, Kmat, config, params, proj_size=None, group=None, ops=None):
+    """GRID_REAS='lstm3d' (model_multi.py:457-462: ReLU -> ConvLSTM over the views -> BN -> ReLU) with the grid split
+    into x-slabs.  ``params``: {'W' [3,3,3,C+F,4F], 'b' [4F], 'bn' optional}.  Every rank holds all views' features
+    (13 MB).  Returns (ray slices or None, this rank's fused slab [B,Xs,Y,Z,F])."""
+    ops = ops or CudaOps()
+    rank, ws = world(group)
+    xb, xc = slab_bounds(config.nvox, rank, ws)
+    if xc < 1:
+        raise ValueError("lstm_slab needs at least one x-plane per rank (nvox=%d, world=%d)" % (config.nvox, ws))
+    lo, hi = (1 if rank > 0 else 0), (1 if rank < ws - 1 else 0)
+    V = feats.shape[1]
+    Rmain = Rcam[:, 0].contiguous()
+    cell = ops.convlstm_cell(params["W"], params["b"])
+    h = c = None
+    for t in range(V):
+        # view t unprojected for the slab and its halo planes; a 1-view 'sum' is the per-view grid itself
+        x_t = ops.unproject_fuse(feats[:, t:t + 1].contiguous(), Rcam[:, t:t + 1].contiguous(), Kmat, config, "sum",
+                                 Rmain=Rmain, x_slab=(xb - lo, xc + lo + hi))
+        h, c = cell.step_slab(x_t, h, c, (lo, hi), relu_in=True)
+        if t + 1 < V:
+            exchange_halo(h, lo, hi, group)
+    slab = ops.affine_relu(h[:, lo:lo + xc], params.get("bn"))
+    if proj_size is None:
+        return None, slab
+    rays = ops.proj_grid(slab, Rcam, Kmat, config, proj_size, x_slab=(xb, xc))
+    rays = _all_reduce(rays, dist.ReduceOp.SUM, group)
+    return rays, slab

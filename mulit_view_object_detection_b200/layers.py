@@ -227,6 +227,30 @@ class ConvLSTMTensorCore:
         return h, c
 
 
+    def step_slab(self, x, h_prev, c_prev, halo, relu_in=False, h_out=None):
+        """Slab form (mvf_convlstm_step_tc_slab): ``x`` [B,lo+Xs+hi,Y,Z,C] and ``h_prev`` / returned ``h`` [B,lo+Xs+hi,Y,Z,F]
+        carry the halo planes ``halo = (lo, hi)``; ``c_prev`` / returned ``c`` are [B,Xs,Y,Z,F].  Only the interior planes
+        of ``h`` are written; the caller fills the halo planes (dist.exchange_halo)."""
+        x = _cuda(x, "x")
+        lo, hi = int(halo[0]), int(halo[1])
+        B, Xin, Y, Z, Cc = x.shape
+        Xs = Xin - lo - hi
+        if Cc != self.C or Xs <= 0:
+            raise ValueError("bad slab: x %s, halo %s, C %d" % (tuple(x.shape), (lo, hi), self.C))
+        need = lib.mvf_convlstm_tc_workspace_bytes(B, Xin, Y, Z, self.C, self.F)
+        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device:
+            self._ws = torch.empty(need // 4, dtype=torch.float32, device=x.device)
+        h = h_out if h_out is not None else torch.zeros((B, Xin, Y, Z, self.F), dtype=torch.float32, device=x.device)
+        c = torch.empty((B, Xs, Y, Z, self.F), dtype=torch.float32, device=x.device)
+        hp = _cuda(h_prev, "h_prev") if h_prev is not None else None
+        cp = _cuda(c_prev, "c_prev") if c_prev is not None else None
+        rc = lib.mvf_convlstm_step_tc_slab(_ptr(x), _ptr(hp), _ptr(cp), _ptr(self.wsplit), _ptr(self.bias), self.forget_bias,
+                                           B, Xs, Y, Z, self.C, self.F, lo, hi, _lib.FLAG_RELU_IN if relu_in else 0,
+                                           _ptr(h), _ptr(c), _ptr(self._ws), self._ws.numel() * 4, _stream())
+        check(rc, "mvf_convlstm_step_tc_slab")
+        return h, c
+
+
 _cells = {}      # one prepared cell per layer name, like the reference's `reused_lay` (model_multi.py:112-117)
 
 

@@ -41,6 +41,36 @@ class OracleOps:
     def scale(self, grid, factor):
         return grid * np.float32(factor)
 
+    def convlstm_cell(self, W, bias):
+        return OracleCell(W.numpy(), bias.numpy())
+
+    def affine_relu(self, h, bn):
+        scale, shift = oracle.batch_norm_affine(*bn)
+        return torch.from_numpy(np.maximum(h.numpy() * scale + shift, 0).astype(np.float32))
+
+
+class OracleCell:
+    """ConvLSTMCell.call on a slab with halo planes: SAME convolution over the padded extent, interior kept."""
+
+    def __init__(self, W, b):
+        self.W, self.b = W, b
+
+    def step_slab(self, x, h_prev, c_prev, halo, relu_in=False):
+        lo, hi = halo
+        xn = x.numpy()
+        B, Xin = xn.shape[:2]
+        F = self.b.shape[0] // 4
+        if relu_in:
+            xn = np.maximum(xn, 0)
+        hp = h_prev.numpy() if h_prev is not None else np.zeros(xn.shape[:4] + (F,), np.float32)
+        cp = np.zeros_like(hp)
+        if c_prev is not None:
+            cp[:, lo:Xin - hi] = c_prev.numpy()
+        h, c = oracle.convlstm_cell_step(xn, cp, hp, self.W, self.b)
+        h_out = np.zeros_like(h)
+        h_out[:, lo:Xin - hi] = h[:, lo:Xin - hi]            # halo planes are the neighbours' to fill
+        return torch.from_numpy(h_out), torch.from_numpy(np.ascontiguousarray(c[:, lo:Xin - hi]))
+
 
 def _free_port():
     s = socket.socket()
@@ -68,6 +98,44 @@ def _worker(rank, world_size, port, strategy, mode, out_dir):
         np.save(os.path.join(out_dir, "rays_%d.npy" % rank), rays.numpy())
     finally:
         dist.destroy_process_group()
+
+
+def _lstm_case():
+    cfg = small_cfg(nvox=6, nvox_z=4, samples=4, NUM_VIEWS=3, GRID_REAS="lstm3d", TOP_DOWN_PYRAMID_SIZE=4)
+    feats, Rcam, Kmat = scene(cfg, 1, 3, 12, 12, 4, seed=8)
+    rng = np.random.default_rng(3)
+    W = (rng.standard_normal((3, 3, 3, 8, 16)) * 0.15).astype(np.float32)
+    b = rng.normal(0, 0.1, 16).astype(np.float32)
+    bn = (np.full(4, 1.1, np.float32), np.full(4, 0.02, np.float32), np.full(4, -0.01, np.float32), np.full(4, 0.9, np.float32))
+    return cfg, feats, Rcam, Kmat, W, b, bn
+
+
+def _lstm_worker(rank, world_size, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from mulit_view_object_detection_b200 import dist as mvd
+        cfg, feats, Rcam, Kmat, W, b, bn = _lstm_case()
+        t = [torch.from_numpy(a) for a in (feats, Rcam, Kmat)]
+        rays, slab = mvd.lstm_slab(*t, cfg, {"W": torch.from_numpy(W), "b": torch.from_numpy(b), "bn": bn}, proj_size=10,
+                                   ops=OracleOps())
+        np.save(os.path.join(out_dir, "rays_%d.npy" % rank), rays.numpy())
+        np.save(os.path.join(out_dir, "slab_%d.npy" % rank), slab.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world_size", [2, 3])
+def test_lstm_slab_halo_exchange_matches_single_process(world_size, tmp_path):
+    """Recurrent fusion over x-slabs with a 1-voxel halo of h exchanged per step == the unsharded recurrence."""
+    mp.spawn(_lstm_worker, args=(world_size, _free_port(), str(tmp_path)), nprocs=world_size, join=True)
+    cfg, feats, Rcam, Kmat, W, b, bn = _lstm_case()
+    fused = oracle.grid_reas(oracle.unproj_feat(feats, Rcam, Kmat, cfg), "grid_reas_P4", cfg, {"W": W, "b": b, "bn": bn})
+    ref = oracle.proj_grid(fused, Rcam, Kmat, cfg, 10)
+    slabs = [np.load(os.path.join(str(tmp_path), "slab_%d.npy" % r)) for r in range(world_size)]
+    np.testing.assert_allclose(np.concatenate(slabs, axis=1), fused, rtol=1e-6, atol=1e-7)
+    for r in range(world_size):
+        np.testing.assert_allclose(np.load(os.path.join(str(tmp_path), "rays_%d.npy" % r)), ref, rtol=1e-6, atol=1e-7)
 
 
 @pytest.mark.parametrize("strategy,mode", [("allreduce", "sum"), ("allreduce", "max"), ("allreduce", "mean"),

@@ -95,3 +95,35 @@ def test_ident_tc_matches_oracle(B, V, X, Y, Z, C, Cout):
     close(out.cpu().numpy(), o, rtol=1e-5, atol=5e-6)
     ref = m.grid_reas(dg, "ident_fp32", cfg, params=params, tensor_cores=False)
     close(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=5e-6)
+
+
+def test_tc_slab_steps_with_halo_match_full_grid():
+    """mvf_convlstm_step_tc_slab: two x-slabs with a 1-voxel halo of x and h (planes copied by hand here, exchanged by
+    dist.exchange_halo in the multi-GPU path) reproduce the full-grid recurrence bit for bit (same tiles, same K order)."""
+    import torch
+    m = _m()
+    rng = np.random.default_rng(11)
+    B, X, Y, Z, C = 1, 6, 4, 8, 64
+    W, b = _weights(rng, C, C)
+    xs = [rng.standard_normal((B, X, Y, Z, C)).astype(np.float32) for _ in range(3)]
+    dW, db = to_dev(W, b)
+    dx = to_dev(*xs)
+    cell = m.ConvLSTMTensorCore(dW, db, 1.0)
+    h = c = None
+    for t in range(3):
+        h, c = cell.step(dx[t], h, c, relu_in=True)
+    # slabs: rank 0 owns x in [0,4) (halo on the high side), rank 1 owns [4,6) (halo on the low side)
+    spans = [(0, 4, 0, 1), (4, 2, 1, 0)]
+    hs, cs = [None, None], [None, None]
+    for t in range(3):
+        new = []
+        for r, (xb, xc, lo, hi) in enumerate(spans):
+            x_pad = dx[t][:, xb - lo:xb + xc + hi].contiguous()
+            new.append(cell.step_slab(x_pad, hs[r], cs[r], (lo, hi), relu_in=True))
+        (h0, c0), (h1, c1) = new
+        h0[:, 4].copy_(h1[:, 1])          # rank 1's first interior plane -> rank 0's high halo
+        h1[:, 0].copy_(h0[:, 3])          # rank 0's last interior plane  -> rank 1's low halo
+        hs, cs = [h0, h1], [c0, c1]
+    got_h = torch.cat([hs[0][:, :4], hs[1][:, 1:]], dim=1)
+    got_c = torch.cat(cs, dim=1)
+    assert torch.equal(got_h, h) and torch.equal(got_c, c)

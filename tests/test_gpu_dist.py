@@ -41,6 +41,19 @@ def _worker(rank, world_size, port, out_dir):
         refm, _ = m.unproject_fuse_project(*d, cfg, 24, mode="max")
         raysm, _ = mvd.view_shard_reduce_scatter(*d, cfg, 24, mode="max")
         res["max_exact"] = float((raysm - refm).abs().max())
+        # recurrent fusion over x-slabs with halo exchange vs the single-GPU grid_reas('lstm3d') + proj_grid
+        rng = np.random.default_rng(4)
+        Cc = 64
+        W = torch.from_numpy((rng.standard_normal((3, 3, 3, 2 * Cc, 4 * Cc)) * 0.02).astype(np.float32)).cuda()
+        bb = torch.from_numpy(rng.normal(0, 0.1, 4 * Cc).astype(np.float32)).cuda()
+        lcfg = small_cfg(nvox=16, nvox_z=16, samples=6, NUM_VIEWS=4, GRID_REAS="lstm3d", TOP_DOWN_PYRAMID_SIZE=Cc)
+        d1 = [t[:1].contiguous() for t in d]
+        full = m.grid_reas(m.unproj_feat(d1, lcfg), "lstm_ref", lcfg, params={"W": W, "b": bb})
+        ref_rays = m.proj_grid([full, d1[1], d1[2]], lcfg, 24)
+        lrays, slab = mvd.lstm_slab(*d1, lcfg, {"W": W, "b": bb}, proj_size=24)
+        xb, xc = mvd.slab_bounds(16, rank, world_size)
+        res["lstm_slab"] = float((slab - full[:, xb:xb + xc]).abs().max())
+        res["lstm_rays"] = float((lrays - ref_rays).abs().max())
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, "res_%d.npy" % rank), np.array([res[k] for k in sorted(res)]))
     finally:
@@ -54,6 +67,8 @@ def test_nccl_strategies_match_single_gpu(tmp_path):
         pytest.skip("needs 2 GPUs")
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
-        allreduce, max_exact, reduce_scatter, scene_err, slab_owner = np.load(os.path.join(str(tmp_path), "res_%d.npy" % r))
+        allreduce, lstm_rays, lstm_slab, max_exact, reduce_scatter, scene_err, slab_owner = \
+            np.load(os.path.join(str(tmp_path), "res_%d.npy" % r))
+        assert lstm_slab == 0.0 and lstm_rays == 0.0        # same tiles, same K order: bit-identical to the unsharded run
         assert allreduce < 1e-5 and reduce_scatter < 1e-5 and slab_owner < 1e-5      # partial-sum order differs
         assert scene_err == 0.0 and max_exact == 0.0
