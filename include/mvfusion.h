@@ -101,6 +101,33 @@ int mvf_ident_fuse(const float* in, const float* weight, const float* bias,
                    const float* bn_scale, const float* bn_shift,
                    int B, int V, long long N, int C, int Cout, float* out, void* stream);
 
+/* ---- the conv3d family on the tensor cores (tcgen05, 3xTF32 split) ---------------------------------
+ * One implicit-GEMM kernel serves every plain 3-D convolution of the fusion path:
+ *   MVF_CONV_S1   Conv3D k=1|3 stride 1 SAME     grid_reas 'ident' (model_multi.py:443-455), depth_sampling 1x1 convs (:472-480)
+ *   MVF_CONV_S2   Conv3D k=3 stride 2 SAME       grid_reas 'conv3d' encoder (:415-428); X,Y,Z must be even
+ *   MVF_DECONV_S2 Conv3DTranspose k=3 stride 2   grid_reas 'conv3d' decoder (:430-441)
+ * in  [B,V,X,Y,Z,C]: V tensors concatenated on channels (view-major, v*C + c) -- the reference's transpose+reshape
+ *     of the per-view grids (:411-413) without moving data;  in2 [B,X,Y,Z,C2] or NULL: appended after them (the skip
+ *     concat of :438).  X,Y,Z are the INPUT dims; out is [B,X,Y,Z,Cout] (S1), [B,X/2,Y/2,Z/2,Cout] (S2) or
+ *     [B,2X,2Y,2Z,Cout] (DECONV).
+ * out = act(bn(conv(pre(in)) + bias)); pre = optional per-input-channel affine pre_scale/pre_shift [V*C] (a depthwise
+ *     1x1 conv, :472,:477) then ReLU when MVF_FLAG_RELU_IN; act = ReLU when MVF_FLAG_RELU_OUT; bn_* [Cout] or NULL.
+ * Weights: mvf_conv3d_prepare(W) once per tensor.  W is the Keras kernel: Conv3D [k,k,k,Cin,Cout], Conv3DTranspose
+ *     [3,3,3,Cout,Cin]; Cin = V*C + C2.  chan_interleave = S > 1: the reference orders the input channels (c*S + s)
+ *     while `in` supplies S sources of C channels (depth_sampling, :468-470).
+ * Needs C % 32 == 0, C2 % 32 == 0, Cout % 16 == 0 (MVF_EUNSUPPORTED otherwise). */
+#define MVF_CONV_S1   0
+#define MVF_CONV_S2   1
+#define MVF_DECONV_S2 2
+size_t mvf_conv3d_wsplit_bytes(int kind, int ksize, int Cin, int Cout);
+int mvf_conv3d_prepare(const float* W, int kind, int ksize, int Cin, int Cout, int chan_interleave,
+                       float* wsplit, void* stream);
+size_t mvf_conv3d_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C, int C2);
+int mvf_conv3d_tc(const float* in, const float* in2, const float* wsplit, const float* bias,
+                  const float* bn_scale, const float* bn_shift, const float* pre_scale, const float* pre_shift,
+                  int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout, int flags,
+                  float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- grid_reas 'ident' on the tensor cores (tcgen05, 3xTF32 split) ------------------------------
  * Same contract as mvf_ident_fuse (model_multi.py:443-455) for C % 32 == 0 and Cout % 16 == 0
  * (MVF_EUNSUPPORTED otherwise: use mvf_ident_fuse); the grid shape is passed as X,Y,Z (N = X*Y*Z).

@@ -14,6 +14,7 @@ MVF_OK = 0
 MVF_EINVAL, MVF_ENULL, MVF_EALIGN, MVF_ECUDA, MVF_EUNSUPPORTED, MVF_EWORKSPACE = -1, -2, -3, -4, -5, -6
 FUSE_NONE, FUSE_SUM, FUSE_MEAN, FUSE_MAX = 0, 1, 2, 3
 FLAG_RELU_IN, FLAG_RELU_OUT, FLAG_WORLD_GRID = 1, 2, 4
+CONV_S1, CONV_S2, DECONV_S2 = 0, 1, 2
 MAX_VIEWS, MAX_DIM, MAX_SAMPLES, MAX_NMS_BOXES, MAX_CLASSES = 32, 192, 64, 8192, 256
 
 
@@ -48,6 +49,10 @@ _SIGS = {
                                 _p, _p, _p, _p, _p, _p, _p]),
     "mvf_view_reduce": (_i, [_p, _i, _i, _ll, _i, _i, _i, _p, _p, _p, _p]),
     "mvf_ident_fuse": (_i, [_p, _p, _p, _p, _p, _i, _i, _ll, _i, _i, _p, _p]),
+    "mvf_conv3d_wsplit_bytes": (_sz, [_i, _i, _i, _i]),
+    "mvf_conv3d_prepare": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "mvf_conv3d_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "mvf_conv3d_tc": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "mvf_ident_wsplit_bytes": (_sz, [_i, _i, _i]),
     "mvf_ident_prepare": (_i, [_p, _i, _i, _i, _p, _p]),
     "mvf_ident_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),

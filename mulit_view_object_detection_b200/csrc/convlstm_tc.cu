@@ -45,7 +45,10 @@ struct TcArgs {
     int BX, BY, BZ, tiles_x, tiles_y, tiles_z;
     int has_h;
     int halo_lo, halo_hi;         // slab mode: x and h_prev / h_out carry halo_lo + X + halo_hi planes in x, c_prev / c_out carry X
-    int V, Cout;                  // ident mode: K = V*C (views concatenated on channels), Cout output channels
+    // plain mode (conv3d family): x = V tensors [B,V,(sub-lattices),X,Y,Z,C] concatenated on channels, then the F channels of `h`
+    int V, Cout;                  // view-sources of x, output channels
+    int kind, ksize;              // MVF_CONV_S1 / _S2 / MVF_DECONV_S2, kernel size per axis (1 or 3)
+    int relu_out;
     const float* bn_scale; const float* bn_shift; float* out;
     int promote;                  // K-chunks per promotion of the partial accumulator into the master (0 = never)
     float forget_bias;
@@ -116,8 +119,37 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // IDENT = false: ConvLSTM step (27 taps, gates in the epilogue).
-// IDENT = true : grid_reas 'ident' (model_multi.py:443-455): 1x1x1 conv over the view-concatenated channels of
-//                [B,V,X,Y,Z,C] -> Cout, + bias -> BN -> ReLU; the same pipeline with one tap per view and a plain epilogue.
+// IDENT = true : the plain conv3d family with a bias -> BN -> ReLU epilogue, on the same pipeline:
+//   MVF_CONV_S1   Conv3D k=1|3, stride 1, SAME.  k=1, V views = grid_reas 'ident' (model_multi.py:443-455).
+//   MVF_CONV_S2   Conv3D k=3, stride 2, SAME on even dims (TF pads only at the high end: in = 2*o + k).  The split pass
+//                 stores the input as its 8 parity sub-lattices, so tap k reads a PLAIN box of sub-lattice (k & 1) shifted by
+//                 (k == 2); the TMA zero fill at the high end is TF's pad_after = 1   (model_multi.py:415-428).
+//   MVF_DECONV_S2 Conv3DTranspose k=3, stride 2, SAME: out[2o + k] += in[o] * W[k].  blockIdx.z = output parity class;
+//                 an even output coordinate gets taps (o, k=0) and (o-1, k=2), an odd one (o, k=1)   (:430-441).
+struct TapRef { int sub, dx, dy, dz, kidx; };
+__device__ __forceinline__ TapRef decode_tap(int kind, int ksize, int cls, int t) {
+    TapRef r = {0, 0, 0, 0, 0};
+    if (kind == MVF_CONV_S1) {
+        if (ksize == 3) { r.dx = t / 9 - 1; r.dy = (t / 3) % 3 - 1; r.dz = t % 3 - 1; r.kidx = t; }
+    } else if (kind == MVF_CONV_S2) {
+        const int kx = t / 9, ky = (t / 3) % 3, kz = t % 3;
+        r.sub = ((kx & 1) * 2 + (ky & 1)) * 2 + (kz & 1);
+        r.dx = kx >> 1; r.dy = ky >> 1; r.dz = kz >> 1; r.kidx = t;
+    } else {                                                 // MVF_DECONV_S2: cls = (px,py,pz); bit j of t picks the second tap of the j-th even axis
+        const int px = (cls >> 2) & 1, py = (cls >> 1) & 1, pz = cls & 1;
+        int bit = 0, kx, ky, kz;
+        if (px) kx = 1; else { const int s2 = (t >> bit) & 1; ++bit; kx = s2 ? 2 : 0; r.dx = -s2; }
+        if (py) ky = 1; else { const int s2 = (t >> bit) & 1; ++bit; ky = s2 ? 2 : 0; r.dy = -s2; }
+        if (pz) kz = 1; else { const int s2 = (t >> bit) & 1; ++bit; kz = s2 ? 2 : 0; r.dz = -s2; }
+        r.kidx = (kx * 3 + ky) * 3 + kz;
+    }
+    return r;
+}
+__device__ __forceinline__ int tap_count(int kind, int ksize, int cls) {
+    if (kind == MVF_DECONV_S2) return 1 << (3 - (((cls >> 2) & 1) + ((cls >> 1) & 1) + (cls & 1)));
+    return ksize == 3 ? 27 : 1;
+}
+
 template <bool IDENT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
@@ -158,9 +190,11 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot) : "memory");
 
     const int cx = a.C / TC_K, ch = a.has_h ? a.F / TC_K : 0;    // 32-channel chunks of x and of h_prev
-    const int per_tap = cx + ch;
-    const int nchunks = IDENT ? a.V * cx : 27 * per_tap;
-    const int CF = a.C + a.F;
+    const int cls = IDENT ? (int)blockIdx.z : 0;                  // output parity class (deconv)
+    const int per_tap = IDENT ? a.V * cx + ch : cx + ch;
+    const int nchunks = IDENT ? tap_count(a.kind, a.ksize, cls) * per_tap : 27 * per_tap;
+    const int CF = IDENT ? a.V * a.C + a.F : a.C + a.F;
+    const int nsub = (IDENT && a.kind == MVF_CONV_S2) ? 8 : 1;
     const int gsz = a.promote > 0 ? a.promote : nchunks;         // K-chunks per partial accumulation chain
     const int ngroups = (nchunks + gsz - 1) / gsz;
 
@@ -172,9 +206,13 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
             mbar_wait(empty_bar(s), phase ^ 1u);
             int dx = 0, dy = 0, dz = 0, c0, krow, bidx = b;
             bool from_h = false;
-            if (IDENT) {                                                                // view v, channel chunk kc: W row v*C + c
-                const int v = it / cx, kc = it - v * cx;
-                c0 = kc * TC_K; krow = v * a.C + c0; bidx = b * a.V + v;
+            if (IDENT) {                                     // tap-major; inside a tap: view 0 chunks, ..., view V-1 chunks, h chunks
+                const int tap = it / per_tap, kc = it - tap * per_tap;
+                const TapRef r = decode_tap(a.kind, a.ksize, cls, tap);
+                dx = r.dx; dy = r.dy; dz = r.dz;
+                from_h = kc >= a.V * cx;
+                if (from_h) { c0 = (kc - a.V * cx) * TC_K; krow = r.kidx * CF + a.V * a.C + c0; bidx = b * nsub + r.sub; }
+                else { const int v = kc / cx; c0 = (kc - v * cx) * TC_K; krow = r.kidx * CF + v * a.C + c0; bidx = (b * a.V + v) * nsub + r.sub; }
             } else {
                 const int tap = it / per_tap, kc = it - tap * per_tap;
                 dx = tap / 9 - 1; dy = (tap / 3) % 3 - 1; dz = tap % 3 - 1;             // W[kx][ky][kz], SAME padding
@@ -249,7 +287,10 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
         const long long vox = (((long long)b * a.X + x) * a.Y + y) * a.Z + z;
         const long long voxh = (((long long)b * (a.X + a.halo_lo + a.halo_hi) + x + a.halo_lo) * a.Y + y) * a.Z + z;   // h_out keeps the halo planes
         if (IDENT) {
-            // out[b, vox, co] = relu(bn(acc + bias))     (model_multi.py:449-455)
+            // out[b, vox_out, co] = relu(bn(acc + bias))     (model_multi.py:449-455, :418-441)
+            long long ovox = vox;
+            if (a.kind == MVF_DECONV_S2)
+                ovox = (((long long)b * (2 * a.X) + 2 * x + ((cls >> 2) & 1)) * (2 * a.Y) + 2 * y + ((cls >> 1) & 1)) * (2 * a.Z) + 2 * z + (cls & 1);
 #pragma unroll 1
             for (int c16 = 0; c16 < TC_N; c16 += 16) {
                 float v[16];
@@ -268,10 +309,10 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
                     for (int i = 0; i < 16; ++i) {
                         float y = v[i] + a.bias[co0 + i];
                         if (a.bn_scale) y = fmaf(y, a.bn_scale[co0 + i], a.bn_shift[co0 + i]);
-                        v[i] = fmaxf(y, 0.f);
+                        v[i] = a.relu_out ? fmaxf(y, 0.f) : y;
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) st4(a.out + vox * a.Cout + co0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                    for (int i = 0; i < 16; i += 4) st4(a.out + ovox * a.Cout + co0 + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
                 }
             }
         } else {
@@ -355,13 +396,54 @@ convlstm_prepare_kernel(const float* __restrict__ W, float* __restrict__ whi, fl
     whi[i] = h; wlo[i] = v - h;
 }
 
-// W [K, N] (reference layout, N fastest) -> K-major [N, K] hi and lo halves (no row permutation).
+// General activation split for the conv3d family: v = relu?(in * pre_scale[ch] + pre_shift[ch]) -> (hi, lo), optionally
+// re-laid out as the 8 parity sub-lattices of a stride-2 conv:  in [NB, X, Y, Z, C] -> out [NB, 8, X/2, Y/2, Z/2, C].
+// pre_scale / pre_shift (NULL = identity) are indexed by (v * C + c) with v = (nb % V): the per-input-channel affine of a
+// depthwise 1x1 conv in front of the GEMM (model_multi.py:472,477).
 __global__ void __launch_bounds__(256)
-transpose_split_kernel(const float* __restrict__ W, float* __restrict__ whi, float* __restrict__ wlo, int K, int N) {
+act_split_kernel(const float4* __restrict__ in, float4* __restrict__ hi, float4* __restrict__ lo, long long n4,
+                 int X, int Y, int Z, int C4, int V, int relu, int s2d, const float4* __restrict__ pre_scale, const float4* __restrict__ pre_shift) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = __ldg(in + i);
+    long long t = i;
+    const int c4 = (int)(t % C4); t /= C4;
+    const int z = (int)(t % Z); t /= Z;
+    const int y = (int)(t % Y); t /= Y;
+    const int x = (int)(t % X); t /= X;                         // t = nb
+    if (pre_scale) {
+        const int ch = (int)(t % V) * C4 + c4;
+        const float4 sc = __ldg(pre_scale + ch), sh = __ldg(pre_shift + ch);
+        v = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+    }
+    if (relu) v = relu4(v);
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    long long o = i;
+    if (s2d) {
+        const int sub = ((x & 1) * 2 + (y & 1)) * 2 + (z & 1);
+        o = ((((t * 8 + sub) * (X / 2) + (x >> 1)) * (Y / 2) + (y >> 1)) * (Z / 2) + (z >> 1)) * C4 + c4;
+    }
+    hi[o] = h; lo[o] = l;
+}
+
+// W [K, N] (reference layout, N fastest) -> K-major [N, K] hi and lo halves.  `transposed`: the Conv3DTranspose kernel
+// layout [taps, N, Cin] (Keras: kernel_size + (filters, input_dim)), K index = tap * Cin + ci.  `S` > 1: the reference's
+// input channel order is (c * S + s) (depth_sampling's reshape, model_multi.py:468-470) while the activations arrive as S
+// sources of C channels: row k = s * C + c reads reference row c * S + s.
+__global__ void __launch_bounds__(256)
+weight_split_kernel(const float* __restrict__ W, float* __restrict__ whi, float* __restrict__ wlo, int K, int N, int transposed, int Cin, int S) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // output element, k fastest
     if (i >= (long long)K * N) return;
     const int k = (int)(i % K), n = (int)(i / K);
-    const float v = W[(long long)k * N + n];
+    long long src;
+    if (transposed) { const int tap = k / Cin, ci = k - tap * Cin; src = ((long long)tap * N + n) * Cin + ci; }
+    else if (S > 1) { const int tap = k / Cin, r = k - tap * Cin, Cc = Cin / S, sidx = r / Cc, c = r - sidx * Cc; src = ((long long)tap * Cin + c * S + sidx) * N + n; }
+    else src = (long long)k * N + n;
+    const float v = W[src];
     const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     whi[i] = h; wlo[i] = v - h;
 }
@@ -460,7 +542,7 @@ extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, co
     a.tiles_z = (Z + a.BZ - 1) / a.BZ; a.tiles_y = (Y + a.BY - 1) / a.BY; a.tiles_x = (X + a.BX - 1) / a.BX;
     a.has_h = h_prev != nullptr; a.forget_bias = forget_bias;
     a.halo_lo = halo_lo; a.halo_hi = halo_hi;
-    a.V = 1; a.Cout = 0; a.bn_scale = nullptr; a.bn_shift = nullptr; a.out = nullptr;
+    a.V = 1; a.Cout = 0; a.kind = 0; a.ksize = 3; a.relu_out = 0; a.bn_scale = nullptr; a.bn_shift = nullptr; a.out = nullptr;
     // K-chunks (of 32) per partial accumulation chain; MVF_TC_PROMOTE overrides (0 = one long chain, for A/B measurement)
     static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
     a.promote = promote_env >= 0 ? promote_env : 8;
@@ -491,60 +573,94 @@ extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const f
                                      ws, ws_bytes, stream);
 }
 
-// ---- grid_reas 'ident' on the tensor cores (model_multi.py:443-455) ---------------------------------------------
-extern "C" size_t mvf_ident_wsplit_bytes(int V, int C, int Cout) {
-    if (V <= 0 || C <= 0 || Cout <= 0) return 0;
-    return (size_t)2 * V * C * Cout * sizeof(float);
+// ---- the plain conv3d family on the tensor cores: grid_reas 'ident' / 'conv3d' (model_multi.py:406-455), depth_sampling
+// 'conv3d' branch (:467-480) ---------------------------------------------------------------------------------------
+static int conv_taps(int kind, int ksize) { return (kind == MVF_CONV_S1 && ksize == 1) ? 1 : 27; }
+
+extern "C" size_t mvf_conv3d_wsplit_bytes(int kind, int ksize, int Cin, int Cout) {
+    if (Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
+    return (size_t)2 * conv_taps(kind, ksize) * Cin * Cout * sizeof(float);
 }
 
-extern "C" int mvf_ident_prepare(const float* weight, int V, int C, int Cout, float* wsplit, void* stream) {
-    if (!weight || !wsplit) return MVF_ENULL;
-    if (V <= 0 || C <= 0 || Cout <= 0) return MVF_EINVAL;
-    if (C % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
-    const long long total = (long long)V * C * Cout;
-    transpose_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(weight, wsplit, wsplit + total, V * C, Cout);
+extern "C" int mvf_conv3d_prepare(const float* W, int kind, int ksize, int Cin, int Cout, int chan_interleave,
+                                  float* wsplit, void* stream) {
+    if (!W || !wsplit) return MVF_ENULL;
+    if (Cin <= 0 || Cout <= 0 || chan_interleave < 0) return MVF_EINVAL;
+    if (kind < MVF_CONV_S1 || kind > MVF_DECONV_S2 || (ksize != 1 && ksize != 3) || (kind != MVF_CONV_S1 && ksize != 3)) return MVF_EINVAL;
+    if (Cin % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
+    if (chan_interleave > 1 && (kind == MVF_DECONV_S2 || Cin % chan_interleave != 0)) return MVF_EINVAL;
+    const int K = conv_taps(kind, ksize) * Cin;
+    const long long total = (long long)K * Cout;
+    weight_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, wsplit, wsplit + total, K, Cout,
+                                                                                       kind == MVF_DECONV_S2, Cin, chan_interleave);
     count_launch();
     return check_launch();
 }
 
-extern "C" size_t mvf_ident_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C) {
-    if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0) return 0;
-    return (size_t)2 * B * V * X * Y * Z * C * sizeof(float);          // hi and lo halves of relu(in)
+extern "C" size_t mvf_conv3d_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C, int C2) {
+    if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || C2 < 0) return 0;
+    return (size_t)2 * B * X * Y * Z * ((size_t)V * C + C2) * sizeof(float);      // hi and lo halves of both sources
 }
 
-extern "C" int mvf_ident_fuse_tc(const float* in, const float* wsplit, const float* bias,
-                                 const float* bn_scale, const float* bn_shift,
-                                 int B, int V, int X, int Y, int Z, int C, int Cout,
-                                 float* out, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsplit, const float* bias,
+                             const float* bn_scale, const float* bn_shift, const float* pre_scale, const float* pre_shift,
+                             int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout, int flags,
+                             float* out, void* ws, size_t ws_bytes, void* stream) {
     if (!in || !wsplit || !bias || !out || !ws) return MVF_ENULL;
-    if ((bn_scale == nullptr) != (bn_shift == nullptr)) return MVF_ENULL;
-    if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || Cout <= 0) return MVF_EINVAL;
-    if (C % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
-    if (!aligned16(in) || !aligned16(wsplit) || !aligned16(ws) || !aligned16(out)) return MVF_EALIGN;
-    if (ws_bytes < mvf_ident_tc_workspace_bytes(B, V, X, Y, Z, C)) return MVF_EWORKSPACE;
+    if ((bn_scale == nullptr) != (bn_shift == nullptr) || (pre_scale == nullptr) != (pre_shift == nullptr)) return MVF_ENULL;
+    if ((in2 == nullptr) != (C2 == 0)) return MVF_EINVAL;
+    if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || C2 < 0 || Cout <= 0) return MVF_EINVAL;
+    if (kind < MVF_CONV_S1 || kind > MVF_DECONV_S2 || (ksize != 1 && ksize != 3) || (kind != MVF_CONV_S1 && ksize != 3)) return MVF_EINVAL;
+    if (C % TC_K != 0 || C2 % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
+    if (kind == MVF_CONV_S2 && ((X | Y | Z) & 1)) return MVF_EUNSUPPORTED;      // odd sizes pad on both sides in TF; not built
+    if (pre_scale && in2) return MVF_EUNSUPPORTED;
+    if (!aligned16(in) || !aligned16(wsplit) || !aligned16(ws) || !aligned16(out) || (in2 && !aligned16(in2)) ||
+        (pre_scale && (!aligned16(pre_scale) || !aligned16(pre_shift)))) return MVF_EALIGN;
+    if (ws_bytes < mvf_conv3d_tc_workspace_bytes(B, V, X, Y, Z, C, C2)) return MVF_EWORKSPACE;
     if (!encode_tiled()) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
-    const long long n = (long long)B * V * X * Y * Z * C;
-    float* xh = (float*)ws; float* xl = xh + n;
-    tf32_split_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)xh, (float4*)xl, n / 4, 1);   // ReLU of :448
+    const int relu_in = (flags & MVF_FLAG_RELU_IN) != 0, s2d = kind == MVF_CONV_S2;
+    const long long n1 = (long long)B * V * X * Y * Z * C, n2 = (long long)B * X * Y * Z * C2;
+    float* xh = (float*)ws; float* xl = xh + n1; float* hh = xl + n1; float* hl = hh + n2;
+    act_split_kernel<<<(unsigned)((n1 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)xh, (float4*)xl, n1 / 4, X, Y, Z, C / 4, V,
+                                                                    relu_in, s2d, (const float4*)pre_scale, (const float4*)pre_shift);
     count_launch();
+    if (in2) {
+        act_split_kernel<<<(unsigned)((n2 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in2, (float4*)hh, (float4*)hl, n2 / 4, X, Y, Z, C2 / 4, 1,
+                                                                        relu_in, s2d, nullptr, nullptr);
+        count_launch();
+    }
+    // M space: the output lattice for a conv, the INPUT lattice for the transposed conv; a 1x1x1 conv has no neighbourhood,
+    // so its voxels are flattened into one axis (full 128-row tiles whatever the grid shape)
+    int MX = X, MY = Y, MZ = Z, nb_mul = 1;
+    if (s2d) { MX = X / 2; MY = Y / 2; MZ = Z / 2; nb_mul = 8; }
+    if (kind == MVF_CONV_S1 && ksize == 1) {
+        const long long flat = (long long)X * Y * Z;
+        if (flat > 2147483647ll) return MVF_EUNSUPPORTED;
+        MX = 1; MY = 1; MZ = (int)flat;
+    }
     TcArgs a;
     a.bias = bias; a.c_prev = nullptr; a.h_out = nullptr; a.c_out = nullptr;
-    a.B = B; a.X = X; a.Y = Y; a.Z = Z; a.C = C; a.F = 0;
-    a.BZ = pow2ceil(Z) < TC_M ? pow2ceil(Z) : TC_M;
-    a.BY = pow2ceil(Y) < TC_M / a.BZ ? pow2ceil(Y) : TC_M / a.BZ;
+    a.B = B; a.X = MX; a.Y = MY; a.Z = MZ; a.C = C; a.F = C2;
+    a.BZ = pow2ceil(MZ) < TC_M ? pow2ceil(MZ) : TC_M;
+    a.BY = pow2ceil(MY) < TC_M / a.BZ ? pow2ceil(MY) : TC_M / a.BZ;
     a.BX = TC_M / (a.BZ * a.BY);
-    a.tiles_z = (Z + a.BZ - 1) / a.BZ; a.tiles_y = (Y + a.BY - 1) / a.BY; a.tiles_x = (X + a.BX - 1) / a.BX;
-    a.has_h = 0; a.forget_bias = 0.f; a.halo_lo = 0; a.halo_hi = 0;
-    a.V = V; a.Cout = Cout; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.out = out;
+    a.tiles_z = (MZ + a.BZ - 1) / a.BZ; a.tiles_y = (MY + a.BY - 1) / a.BY; a.tiles_x = (MX + a.BX - 1) / a.BX;
+    a.has_h = in2 != nullptr; a.forget_bias = 0.f; a.halo_lo = 0; a.halo_hi = 0;
+    a.V = V; a.Cout = Cout; a.kind = kind; a.ksize = ksize; a.relu_out = (flags & MVF_FLAG_RELU_OUT) != 0;
+    a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.out = out;
     static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
     a.promote = promote_env >= 0 ? promote_env : 8;
-    const int K = V * C;
+    const int K = conv_taps(kind, ksize) * (V * C + C2);
     const float* whi = wsplit; const float* wlo = wsplit + (long long)K * Cout;
-    CUtensorMap tm_xh, tm_xl, tm_wh, tm_wl;
-    bool ok = make_act_map(&tm_xh, xh, B * V, X, Y, Z, C, a.BX, a.BY, a.BZ) && make_act_map(&tm_xl, xl, B * V, X, Y, Z, C, a.BX, a.BY, a.BZ) &&
+    CUtensorMap tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl;
+    bool ok = make_act_map(&tm_xh, xh, B * V * nb_mul, MX, MY, MZ, C, a.BX, a.BY, a.BZ) &&
+              make_act_map(&tm_xl, xl, B * V * nb_mul, MX, MY, MZ, C, a.BX, a.BY, a.BZ) &&
               make_w_map(&tm_wh, whi, K, Cout) && make_w_map(&tm_wl, wlo, K, Cout);
+    if (ok && in2) ok = make_act_map(&tm_hh, hh, B * nb_mul, MX, MY, MZ, C2, a.BX, a.BY, a.BZ) &&
+                        make_act_map(&tm_hl, hl, B * nb_mul, MX, MY, MZ, C2, a.BX, a.BY, a.BZ);
     if (!ok) return MVF_ECUDA;
+    if (!in2) { tm_hh = tm_xh; tm_hl = tm_xl; }
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(convlstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
@@ -553,8 +669,24 @@ extern "C" int mvf_ident_fuse_tc(const float* in, const float* wsplit, const flo
     const long long mtiles = (long long)B * a.tiles_x * a.tiles_y * a.tiles_z;
     const int ntiles = (Cout + TC_N - 1) / TC_N;
     if (mtiles > 2147483647ll || ntiles > 65535) return MVF_EUNSUPPORTED;
-    dim3 grid((unsigned)mtiles, ntiles);
-    convlstm_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_xh, tm_xl, tm_wh, tm_wl, a);
+    dim3 grid((unsigned)mtiles, ntiles, kind == MVF_DECONV_S2 ? 8 : 1);
+    convlstm_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
     count_launch();
     return check_launch();
+}
+
+// grid_reas 'ident' (model_multi.py:443-455) = the 1x1x1 member of the family: ReLU -> conv over V*C channels -> bias -> BN -> ReLU
+extern "C" size_t mvf_ident_wsplit_bytes(int V, int C, int Cout) { return mvf_conv3d_wsplit_bytes(MVF_CONV_S1, 1, V * C, Cout); }
+extern "C" int mvf_ident_prepare(const float* weight, int V, int C, int Cout, float* wsplit, void* stream) {
+    if (V <= 0 || C <= 0) return MVF_EINVAL;
+    if (C % TC_K != 0) return MVF_EUNSUPPORTED;
+    return mvf_conv3d_prepare(weight, MVF_CONV_S1, 1, V * C, Cout, 0, wsplit, stream);
+}
+extern "C" size_t mvf_ident_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C) { return mvf_conv3d_tc_workspace_bytes(B, V, X, Y, Z, C, 0); }
+extern "C" int mvf_ident_fuse_tc(const float* in, const float* wsplit, const float* bias,
+                                 const float* bn_scale, const float* bn_shift,
+                                 int B, int V, int X, int Y, int Z, int C, int Cout,
+                                 float* out, void* ws, size_t ws_bytes, void* stream) {
+    return mvf_conv3d_tc(in, nullptr, wsplit, bias, bn_scale, bn_shift, nullptr, nullptr, MVF_CONV_S1, 1, B, V, X, Y, Z, C, 0, Cout,
+                         MVF_FLAG_RELU_IN | MVF_FLAG_RELU_OUT, out, ws, ws_bytes, stream);
 }

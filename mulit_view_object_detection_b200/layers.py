@@ -289,6 +289,114 @@ class IdentTensorCore:
 _idents = {}
 
 
+class Conv3dTensorCore:
+    """One plain 3-D convolution of the fusion path on the tensor cores (``mvf_conv3d_tc``): Conv3D k=1|3 stride 1,
+    Conv3D k=3 stride 2, or Conv3DTranspose k=3 stride 2, all 'same' padded, with bias -> BN -> ReLU in the epilogue
+    (model_multi.py:415-441, :443-455, :472-480).  ``W`` is the Keras kernel; it is split / transposed once."""
+
+    KINDS = {"conv": _lib.CONV_S1, "conv_s2": _lib.CONV_S2, "deconv_s2": _lib.DECONV_S2}
+
+    def __init__(self, W, bias, kind, V=1, C2=0, bn=None, chan_interleave=0):
+        W = _cuda(W, "W")
+        self.kind = self.KINDS[kind]
+        if W.dim() == 2:
+            W = W.reshape((1, 1, 1) + tuple(W.shape))
+        self.ksize = int(W.shape[0])
+        if self.kind == _lib.DECONV_S2:
+            self.Cout, Cin = int(W.shape[3]), int(W.shape[4])
+        else:
+            Cin, self.Cout = int(W.shape[3]), int(W.shape[4])
+        if (Cin - C2) % V:
+            raise ValueError("input channels %d - %d do not split into %d views" % (Cin, C2, V))
+        self.V, self.C, self.C2, self.Cin = V, (Cin - C2) // V, C2, Cin
+        self.bias = _cuda(bias, "bias")
+        self.scale, self.shift = _bn_affine(bn, self.Cout, W.device)
+        nbytes = lib.mvf_conv3d_wsplit_bytes(self.kind, self.ksize, Cin, self.Cout)
+        self.wsplit = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=W.device)
+        check(lib.mvf_conv3d_prepare(_ptr(W), self.kind, self.ksize, Cin, self.Cout, int(chan_interleave), _ptr(self.wsplit),
+                                     _stream()), "mvf_conv3d_prepare")
+        self._ws = None
+
+    def out_dims(self, X, Y, Z):
+        if self.kind == _lib.CONV_S2:
+            return X // 2, Y // 2, Z // 2
+        if self.kind == _lib.DECONV_S2:
+            return 2 * X, 2 * Y, 2 * Z
+        return X, Y, Z
+
+    def __call__(self, x, x2=None, relu_in=False, relu_out=True, pre=None):
+        """x [B,V,X,Y,Z,C] (or [B,X,Y,Z,C] when V == 1); x2 [B,X,Y,Z,C2] appended on channels; ``pre`` = (scale, shift)
+        per input channel [V*C] applied before the conv (a depthwise 1x1)."""
+        x = _cuda(x, "x")
+        if x.dim() == 5:
+            x = x.unsqueeze(1)
+        B, V, X, Y, Z, Cc = x.shape
+        if V != self.V or Cc != self.C or (x2 is None) != (self.C2 == 0):
+            raise ValueError("input %s does not match the prepared weights (V=%d, C=%d, C2=%d)" % (tuple(x.shape), self.V, self.C, self.C2))
+        if x2 is not None:
+            x2 = _cuda(x2, "x2")
+            if tuple(x2.shape) != (B, X, Y, Z, self.C2):
+                raise ValueError("x2 must be %s" % ((B, X, Y, Z, self.C2),))
+        need = lib.mvf_conv3d_tc_workspace_bytes(B, V, X, Y, Z, Cc, self.C2)
+        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device:
+            self._ws = torch.empty(need // 4, dtype=torch.float32, device=x.device)
+        OX, OY, OZ = self.out_dims(X, Y, Z)
+        out = torch.empty((B, OX, OY, OZ, self.Cout), dtype=torch.float32, device=x.device)
+        ps = psh = None
+        if pre is not None:
+            ps, psh = _cuda(pre[0], "pre_scale"), _cuda(pre[1], "pre_shift")
+        flags = (_lib.FLAG_RELU_IN if relu_in else 0) | (_lib.FLAG_RELU_OUT if relu_out else 0)
+        rc = lib.mvf_conv3d_tc(_ptr(x), _ptr(x2), _ptr(self.wsplit), _ptr(self.bias), _ptr(self.scale), _ptr(self.shift),
+                               _ptr(ps), _ptr(psh), self.kind, self.ksize, B, V, X, Y, Z, Cc, self.C2, self.Cout, flags,
+                               _ptr(out), _ptr(self._ws), self._ws.numel() * 4, _stream())
+        check(rc, "mvf_conv3d_tc")
+        return out
+
+
+_convs = {}
+
+
+def _cached_conv(name, p, kind, **kw):
+    W = p["W"]
+    key = (W.data_ptr() if isinstance(W, torch.Tensor) else id(W), getattr(W, "_version", 0), kind, tuple(sorted(kw.items())))
+    hit = _convs.get(name)
+    if hit is None or hit[0] != key:
+        hit = (key, Conv3dTensorCore(p["W"], p["b"], kind, bn=p.get("bn", _default_bn(int(np.prod(p["b"].shape)))), **kw))
+        _convs[name] = hit
+    return hit[1]
+
+
+def unet_fuse(x, scope, config, params):
+    """``GRID_REAS='conv3d'`` (model_multi.py:406-441): the MLF U-Net over the view-concatenated grids, four tensor-core
+    convolutions; the per-view grids [B,V,X,Y,Z,C] are consumed in place (no transpose / reshape / concat copies)."""
+    x = _cuda(x, "inputs")
+    B, V, X, Y, Z, Cc = x.shape
+    if X % 4 or Y % 4 or Z % 4:
+        raise ValueError("the conv3d U-Net halves the grid twice: nvox and nvox_z must be multiples of 4")
+    name = scope + "_3D_conv"
+    conv1 = _cached_conv(name + "_1", params["conv1"], "conv_s2", V=V)(x, relu_in=True)               # :415-421
+    conv2 = _cached_conv(name + "_2", params["conv2"], "conv_s2")(conv1)                                # :423-428
+    deconv1 = _cached_conv(name + "_deconv_1", params["deconv1"], "deconv_s2")(conv2)                   # :430-436
+    C2 = conv1.shape[-1]
+    return _cached_conv(name + "_deconv_2", params["deconv2"], "deconv_s2", C2=C2)(deconv1, x2=conv1)   # :437-441
+
+
+def depth_sampling_conv3d(x, name, params):
+    """``depth_sampling`` 'conv3d' branch (model_multi.py:467-480): the [B,S,P,P,C] ray slices are S sources of C channels
+    for a 1x1 conv over C*S inputs (the reference's channel order c*S+s is folded into the prepared weights), each conv
+    preceded by its depthwise 1x1 (a per-channel affine applied while the operand is split)."""
+    x = _cuda(x, "x")
+    B, S, P1, P2, Cc = x.shape
+    dev = x.device
+    dw1w = _cuda(params["dw1"]["w"], "dw1.w").reshape(Cc, S).t().contiguous().reshape(-1)      # (c*S+s) -> (s*C+c)
+    dw1b = _cuda(params["dw1"]["b"], "dw1.b").reshape(Cc, S).t().contiguous().reshape(-1)
+    c1 = _cached_conv(name + "2DConv_1", params["conv1"], "conv", V=S, chan_interleave=S)
+    y = c1(x.reshape(B, S, 1, P1, P2, Cc), pre=(dw1w, dw1b))                                     # :472-475
+    c2 = _cached_conv(name + "2DConv_2", params["conv2"], "conv")
+    y = c2(y, pre=(_cuda(params["dw2"]["w"], "dw2.w"), _cuda(params["dw2"]["b"], "dw2.b")))       # :477-480
+    return y.reshape(B, P1, P2, -1)
+
+
 def convlstm(grid, name, kernel=(3, 3, 3), filters=32, params=None, relu_in=False, tensor_cores=None):
     """``convlstm(grid, name, kernel, filters)`` (model_multi.py:109-123): ConvRNN3D over the view
     axis with zero initial state, last output only.  Weights: ``weights[name] = {'W','b'}``."""
@@ -345,12 +453,14 @@ def grid_reas(inputs, scope, config, kernel=(3, 3, 3), params=None, tensor_cores
                                 B, V, X * Y * Z, Cc, Cout, _ptr(out), _stream())
         check(rc, "mvf_ident_fuse")
         return out
+    if mode == "conv3d":
+        return unet_fuse(x, scope, config, p)
     if mode == "lstm3d":
         h = convlstm(x, scope + "_convlstm3d", kernel=kernel, filters=config.TOP_DOWN_PYRAMID_SIZE,
                      params={"W": p["W"], "b": p["b"]} if "W" in p else None, relu_in=True)
         scale, shift = _bn_affine(p.get("bn", _default_bn(h.shape[-1])), h.shape[-1], h.device)
         return _affine_relu(h, scale, shift)
-    raise ValueError("GRID_REAS=%r is not built (hot path: add, mean, max, ident, lstm3d)" % (mode,))
+    raise ValueError("GRID_REAS=%r is not built (hot path: add, mean, max, ident, conv3d, lstm3d)" % (mode,))
 
 
 def _affine_relu(h, scale, shift):
@@ -435,7 +545,10 @@ def depth_sampling(x, config, name, params=None):
     """``depth_sampling(x, config, name)`` non-conv3d branch: [B,S,P,P,C] -> [B,P,P,C]
     (model_multi.py:481-487).  Weights: ``{'weight' [S], 'bias', 'bn' (4 scalars)}``."""
     if config.GRID_REAS == "conv3d":
-        raise ValueError("depth_sampling conv3d branch is not built (SURVEY.md section 8(f) rank 2)")
+        p = params if params is not None else weights.get(name)
+        if p is None:
+            raise ValueError("no weights registered for depth_sampling %r" % name)
+        return depth_sampling_conv3d(x, name, p)
     x = _cuda(x, "x")
     B, S, P1, P2, Cc = x.shape
     w, bias, inv, shift = _depth_params(name, params, S, x.device)

@@ -96,6 +96,90 @@ def conv3d_same(x, W):
     return y
 
 
+def _same_pad(n, k, s):
+    """TensorFlow 'SAME': out = ceil(n/s); total = max((out-1)*s + k - n, 0); the odd element goes to the END."""
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return out, total // 2, total - total // 2
+
+
+def conv3d_strided_same(x, W, stride):
+    """``KL.Conv3D(strides=stride, padding='same')`` without bias (model_multi.py:415-428): TF 'SAME' padding (for an
+    even size, k=3, stride 2: nothing before, one zero after, i.e. ``in = 2*o + k``).  x [B,X,Y,Z,Cin],
+    W [kx,ky,kz,Cin,Cout] (cross-correlation, as TF).  float64 accumulation."""
+    x = np.asarray(x, dtype=np.float64)
+    W = np.asarray(W, dtype=np.float64)
+    B, X, Y, Z, Cin = x.shape
+    kx, ky, kz, _, Cout = W.shape
+    (ox, bx, ax), (oy, by, ay), (oz, bz, az) = _same_pad(X, kx, stride), _same_pad(Y, ky, stride), _same_pad(Z, kz, stride)
+    xp = np.zeros((B, X + bx + ax, Y + by + ay, Z + bz + az, Cin))
+    xp[:, bx:bx + X, by:by + Y, bz:bz + Z] = x
+    y = np.zeros((B, ox, oy, oz, Cout))
+    for a in range(kx):
+        for b_ in range(ky):
+            for c in range(kz):
+                y += xp[:, a:a + (ox - 1) * stride + 1:stride, b_:b_ + (oy - 1) * stride + 1:stride,
+                        c:c + (oz - 1) * stride + 1:stride] @ W[a, b_, c]
+    return y
+
+
+def conv3d_transpose_same(x, Wt, stride):
+    """``KL.Conv3DTranspose(strides=stride, padding='same')`` without bias (model_multi.py:430-441) =
+    ``tf.nn.conv3d_transpose``: the gradient of the forward SAME convolution (of the 2x-sized tensor) with respect to
+    its input, so ``out[s*o + k - pad_before] += x[o] . Wt[k]`` with the FORWARD conv's pad_before (0 for k=3, stride 2),
+    output size ``stride * in``.  Wt is the Keras kernel [kx,ky,kz,Cout,Cin]."""
+    x = np.asarray(x, dtype=np.float64)
+    Wt = np.asarray(Wt, dtype=np.float64)
+    B, X, Y, Z, Cin = x.shape
+    kx, ky, kz, Cout, _ = Wt.shape
+    OX, OY, OZ = X * stride, Y * stride, Z * stride
+    pbx, pby, pbz = _same_pad(OX, kx, stride)[1], _same_pad(OY, ky, stride)[1], _same_pad(OZ, kz, stride)[1]
+    big = np.zeros((B, OX + kx, OY + ky, OZ + kz, Cout))
+    for a in range(kx):
+        for b_ in range(ky):
+            for c in range(kz):
+                big[:, a:a + X * stride:stride, b_:b_ + Y * stride:stride, c:c + Z * stride:stride] += x @ Wt[a, b_, c].T
+    return big[:, pbx:pbx + OX, pby:pby + OY, pbz:pbz + OZ]
+
+
+def _conv_bn_relu(y, bias, bn):
+    y = (y + np.asarray(bias, np.float64)).astype(F32)
+    if bn is not None:
+        scale, shift = batch_norm_affine(*bn)
+        y = y * scale + shift
+    return np.maximum(y, F32(0)).astype(F32)
+
+
+def unet_fuse(grids, params):
+    """``GRID_REAS='conv3d'`` (model_multi.py:406-441), the MLF-style U-Net: views concatenated on channels
+    (view-major, :411-413) -> ReLU -> Conv3D(2F,s2) -> Conv3D(4F,s2) -> Conv3DTranspose(2F,s2) -> concat with the first
+    encoder output (deconv first, :438) -> Conv3DTranspose(F,s2); BN + ReLU after every conv.
+    params: {'conv1','conv2','deconv1','deconv2'} each {'W','b','bn' optional}."""
+    grids = np.asarray(grids, dtype=F32)
+    B, V, X, Y, Z, C = grids.shape
+    x = np.transpose(grids, (0, 2, 3, 4, 1, 5)).reshape(B, X, Y, Z, V * C)
+    x = np.maximum(x, F32(0))
+    p = params
+    conv1 = _conv_bn_relu(conv3d_strided_same(x, p["conv1"]["W"], 2), p["conv1"]["b"], p["conv1"].get("bn"))
+    conv2 = _conv_bn_relu(conv3d_strided_same(conv1, p["conv2"]["W"], 2), p["conv2"]["b"], p["conv2"].get("bn"))
+    deconv1 = _conv_bn_relu(conv3d_transpose_same(conv2, p["deconv1"]["W"], 2), p["deconv1"]["b"], p["deconv1"].get("bn"))
+    cat = np.concatenate([deconv1, conv1], axis=4)
+    return _conv_bn_relu(conv3d_transpose_same(cat, p["deconv2"]["W"], 2), p["deconv2"]["b"], p["deconv2"].get("bn"))
+
+
+def depth_sampling_conv3d(x, params):
+    """``depth_sampling`` 'conv3d' branch (model_multi.py:467-480): [B,S,P,P,C] -> [B,P,P,C*S] (channel c*S + s) ->
+    DepthwiseConv2D 1x1 -> Conv2D 1x1 (512) -> BN -> ReLU -> DepthwiseConv2D 1x1 -> Conv2D 1x1 (F) -> BN -> ReLU.
+    params: 'dw1' {'w' [C*S], 'b' [C*S]}, 'conv1' {'W' [C*S,512], 'b', 'bn'}, 'dw2' {'w' [512], 'b'}, 'conv2' {'W' [512,F], 'b', 'bn'}."""
+    x = np.asarray(x, dtype=F32)
+    B, S, P1, P2, C = x.shape
+    y = np.transpose(x, (0, 2, 3, 4, 1)).reshape(B, P1, P2, C * S)
+    y = y * np.asarray(params["dw1"]["w"], F32) + np.asarray(params["dw1"]["b"], F32)
+    y = _conv_bn_relu(y.astype(np.float64) @ np.asarray(params["conv1"]["W"], np.float64), params["conv1"]["b"], params["conv1"].get("bn"))
+    y = y * np.asarray(params["dw2"]["w"], F32) + np.asarray(params["dw2"]["b"], F32)
+    return _conv_bn_relu(y.astype(np.float64) @ np.asarray(params["conv2"]["W"], np.float64), params["conv2"]["b"], params["conv2"].get("bn"))
+
+
 def convlstm_cell_step(x, c_prev, h_prev, W, bias, forget_bias=1.0):
     """One ``ConvLSTMCell.call`` (mrcnn/recurrent.py:442-479, normalize=False):
     ``y = conv3d_SAME([x ; h_prev], W) + b``; gates split in the order
@@ -130,6 +214,7 @@ def grid_reas(grids, scope, cfg, params=None):
       add    : {'bn': (gamma,beta,mean,var)}
       ident  : {'weight' [V*C,Cout], 'bias' [Cout], 'bn': ...}
       lstm3d : {'W' [3,3,3,C+F,4F], 'b' [4F], 'bn': ...}
+      conv3d : {'conv1','conv2','deconv1','deconv2'} each {'W','b','bn'} (see :func:`unet_fuse`)
       mean / max (oracle-defined, no BN in the reference): optional 'bn'."""
     params = params or {}
     mode = cfg.GRID_REAS
@@ -146,6 +231,8 @@ def grid_reas(grids, scope, cfg, params=None):
         return x.astype(F32)
     if mode == "ident":
         return ident_fuse(grids, params["weight"], params["bias"], bn)
+    if mode == "conv3d":
+        return unet_fuse(grids, params)
     if mode == "lstm3d":
         x = np.maximum(np.asarray(grids, F32), F32(0))          # :459
         h = convlstm(x, params["W"], params["b"])               # :460

@@ -1,0 +1,118 @@
+"""GPU parity of the tensor-core conv3d family (mvf_conv3d_tc: Conv3D stride 1 / stride 2, Conv3DTranspose stride 2) against
+the oracle restatement of the Keras/TF layers the reference uses in grid_reas 'conv3d' (mrcnn/model_multi.py:406-441) and in
+the depth_sampling 'conv3d' branch (:467-480).
+
+Tolerance: the reference convolves in fp32; the 3xTF32 split carries ~2^-21 per product and the oracle accumulates in float64,
+so outputs (O(1) magnitude after BN + ReLU) are compared at rtol=1e-5, atol=5e-6."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import to_dev, close, small_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def _m():
+    import mulit_view_object_detection_b200 as m
+    return m
+
+
+def _bn(rng, n):
+    return (rng.uniform(0.8, 1.2, n).astype(np.float32), rng.normal(0, 0.05, n).astype(np.float32),
+            rng.normal(0, 0.05, n).astype(np.float32), rng.uniform(0.7, 1.3, n).astype(np.float32))
+
+
+def _layer(rng, shape, fan_in, nout):
+    return {"W": (rng.standard_normal(shape) * np.sqrt(1.0 / fan_in)).astype(np.float32),
+            "b": rng.normal(0, 0.1, nout).astype(np.float32), "bn": _bn(rng, nout)}
+
+
+def _dev_params(p):
+    out = {}
+    for k, v in p.items():
+        out[k] = {kk: (to_dev(vv)[0] if kk in ("W", "b", "w") else vv) for kk, vv in v.items()}
+    return out
+
+
+@pytest.mark.parametrize("X,Y,Z,Cin,Cout", [(4, 4, 8, 32, 32), (6, 4, 10, 64, 48), (2, 8, 4, 32, 272)])
+def test_conv3d_stride2_matches_oracle(X, Y, Z, Cin, Cout):
+    m = _m()
+    rng = np.random.default_rng(X * Cout)
+    p = _layer(rng, (3, 3, 3, Cin, Cout), 27 * Cin, Cout)
+    x = rng.standard_normal((2, X, Y, Z, Cin)).astype(np.float32)
+    conv = m.Conv3dTensorCore(*to_dev(p["W"], p["b"]), "conv_s2", bn=p["bn"])
+    got = conv(to_dev(x)[0], relu_in=True)
+    ref = oracle.fusion._conv_bn_relu(oracle.conv3d_strided_same(np.maximum(x, 0), p["W"], 2), p["b"], p["bn"])
+    assert tuple(got.shape) == ref.shape
+    close(got.cpu().numpy(), ref, rtol=1e-5, atol=5e-6)
+
+
+@pytest.mark.parametrize("X,Y,Z,Cin,Cout", [(2, 2, 4, 32, 32), (3, 2, 5, 64, 48), (1, 4, 2, 32, 272)])
+def test_conv3d_transpose_stride2_matches_oracle(X, Y, Z, Cin, Cout):
+    m = _m()
+    rng = np.random.default_rng(Z * Cout)
+    p = _layer(rng, (3, 3, 3, Cout, Cin), 8 * Cin, Cout)          # Keras Conv3DTranspose kernel: [k,k,k,filters,in]
+    x = rng.standard_normal((2, X, Y, Z, Cin)).astype(np.float32)
+    conv = m.Conv3dTensorCore(*to_dev(p["W"], p["b"]), "deconv_s2", bn=p["bn"])
+    got = conv(to_dev(x)[0])
+    ref = oracle.fusion._conv_bn_relu(oracle.conv3d_transpose_same(x, p["W"], 2), p["b"], p["bn"])
+    assert tuple(got.shape) == ref.shape
+    close(got.cpu().numpy(), ref, rtol=1e-5, atol=5e-6)
+
+
+def test_conv3d_stride1_matches_oracle():
+    m = _m()
+    rng = np.random.default_rng(2)
+    p = _layer(rng, (3, 3, 3, 32, 64), 27 * 32, 64)
+    x = rng.standard_normal((1, 3, 5, 6, 32)).astype(np.float32)
+    conv = m.Conv3dTensorCore(*to_dev(p["W"], p["b"]), "conv", bn=p["bn"])
+    got = conv(to_dev(x)[0], relu_out=False)
+    y = (oracle.fusion.conv3d_same(x, p["W"]) + p["b"]).astype(np.float32)
+    scale, shift = oracle.batch_norm_affine(*p["bn"])
+    close(got.cpu().numpy(), y * scale + shift, rtol=1e-5, atol=5e-6)
+
+
+def test_stride2_rejects_odd_dims():
+    m = _m()
+    rng = np.random.default_rng(0)
+    p = _layer(rng, (3, 3, 3, 32, 32), 27 * 32, 32)
+    conv = m.Conv3dTensorCore(*to_dev(p["W"], p["b"]), "conv_s2")
+    with pytest.raises(ValueError):
+        conv(to_dev(rng.standard_normal((1, 3, 4, 4, 32)).astype(np.float32))[0])
+
+
+@pytest.mark.parametrize("B,V,X,Z,C,F", [(1, 3, 8, 8, 32, 32), (2, 2, 4, 12, 32, 16)])
+def test_grid_reas_conv3d_unet(B, V, X, Z, C, F):
+    """grid_reas('conv3d') (model_multi.py:406-441): U-Net over the view-concatenated grids."""
+    m = _m()
+    rng = np.random.default_rng(V * 10 + Z)
+    cfg = small_cfg(GRID_REAS="conv3d", NUM_VIEWS=V, nvox=X, nvox_z=Z, TOP_DOWN_PYRAMID_SIZE=F)
+    grids = rng.standard_normal((B, V, X, X, Z, C)).astype(np.float32)
+    params = {"conv1": _layer(rng, (3, 3, 3, V * C, 2 * F), 27 * V * C, 2 * F),
+              "conv2": _layer(rng, (3, 3, 3, 2 * F, 4 * F), 27 * 2 * F, 4 * F),
+              "deconv1": _layer(rng, (3, 3, 3, 2 * F, 4 * F), 8 * 4 * F, 2 * F),
+              "deconv2": _layer(rng, (3, 3, 3, F, 4 * F), 8 * 4 * F, F)}
+    n0 = m.launch_count()
+    out = m.grid_reas(to_dev(grids)[0], "unet_%d_%d" % (V, Z), cfg, params=_dev_params(params))
+    ref = oracle.grid_reas(grids, "grid_reas_P4", cfg, params)
+    assert tuple(out.shape) == (B, X, X, Z, F)
+    close(out.cpu().numpy(), ref, rtol=1e-5, atol=5e-6)
+    assert m.launch_count() - n0 >= 4 + 4 + 5          # 4 weight preparations, 4 GEMM launches, 5 operand split passes
+
+
+def test_depth_sampling_conv3d_branch():
+    """depth_sampling 'conv3d' branch (model_multi.py:467-480): depthwise 1x1 -> 1x1 conv (512) -> BN -> ReLU, twice."""
+    m = _m()
+    rng = np.random.default_rng(6)
+    B, S, P, C, H, F = 2, 4, 6, 32, 64, 32
+    cfg = small_cfg(GRID_REAS="conv3d", samples=S, TOP_DOWN_PYRAMID_SIZE=F)
+    x = np.maximum(rng.standard_normal((B, S, P, P, C)), 0).astype(np.float32)
+    params = {"dw1": {"w": rng.uniform(0.5, 1.5, C * S).astype(np.float32), "b": rng.normal(0, 0.1, C * S).astype(np.float32)},
+              "conv1": _layer(rng, (C * S, H), C * S, H),
+              "dw2": {"w": rng.uniform(0.5, 1.5, H).astype(np.float32), "b": rng.normal(0, 0.1, H).astype(np.float32)},
+              "conv2": _layer(rng, (H, F), H, F)}
+    out = m.depth_sampling(to_dev(x)[0], cfg, "PG4_depth", params=_dev_params(params))
+    ref = oracle.depth_sampling_conv3d(x, params)
+    assert tuple(out.shape) == (B, P, P, F)
+    close(out.cpu().numpy(), ref, rtol=1e-5, atol=5e-6)
