@@ -37,13 +37,13 @@ def make_config(B):
 
 
 def workload_config(args, n_gpus):
-    return {"workload": "T: %d-view scene, 256-ch P4 40x40 features, 64^3 grid, unproject->sum-fuse->project(P=40,S=20), fp32"
-                        % T["V"],
+    return {"workload": "T: %d-view scene, 256-ch P4 40x40 features, %d^3 grid, unproject->sum-fuse->project(P=40,S=20), fp32"
+                        % (T["V"], T["nvox"]),
             "scenes_per_gpu": args.scenes, "views": T["V"], "grid": [T["nvox"]] * 3, "channels": T["C"],
             "feature_hw": [T["fh"], T["fw"]], "proj": T["P"], "samples": T["S"],
             "sharding": "scenes sharded across ranks, no data-path collective" if n_gpus > 1 else "single GPU",
-            "l2_policy": "inputs larger than L2: per-step working set = %d scenes x 347 MB (features %.0f MB, grids %.0f MB)"
-                         % (args.scenes, args.scenes * 13.1, args.scenes * 268.4)}
+            "l2_policy": "inputs larger than L2: per-step working set = %d scenes x %.0f MB (features %.0f MB, grids %.0f MB)"
+                         % (args.scenes, sum(algorithmic_bytes(1)) / 1e6, args.scenes * 13.1, args.scenes * T["nvox"] ** 3 * 1024 / 1e6)}
 
 
 def algorithmic_bytes(B):
@@ -394,8 +394,8 @@ def run_cooperative(args):
         cfgd = workload_config(args, world)
         cfgd["sharding"] = args.strategy
         if args.strategy == "lstm_slab":
-            cfgd["workload"] = "c3: %d-view scene, 64^3 grid, recurrent voxel fusion (ConvLSTM 3x3x3, C=F=256, 3xTF32 on tcgen05), " \
-                               "x-slabs + 1-voxel halo of h exchanged per step, then proj_grid" % T["V"]
+            cfgd["workload"] = "c3: %d-view scene, %d^3 grid, recurrent voxel fusion (ConvLSTM 3x3x3, C=F=256, 3xTF32 on tcgen05), " \
+                               "x-slabs + 1-voxel halo of h exchanged per step, then proj_grid" % (T["V"], T["nvox"])
             flop = 2.0 * T["nvox"] ** 3 * 27 * 2 * T["C"] * 4 * T["C"] * T["V"] * B
             extra = {"useful_tflops": flop * args.steps / (total_ms * 1e-3) / 1e12}
         else:
@@ -421,7 +421,9 @@ def main():
     ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner", "lstm_slab"],
                     help="multi-GPU sharding: scene (default, weak scaling, no collective) or one of the cooperative "
                          "strategies of dist.py on a FIXED batch of --scenes scenes (strong scaling)")
+    ap.add_argument("--nvox", type=int, default=64, help="voxels per grid axis (64 = workload T; 96 = config c5)")
     args = ap.parse_args()
+    T["nvox"] = args.nvox
     if args.impl == "reference":
         return run_reference(args)
     if args.strategy != "scene":

@@ -20,6 +20,7 @@ class FusionConfig:
 
     # voxel grid (interior_multi.py:379-389)
     GRID_REAS = "add"
+    VANILLA = False          # interior_multi.py:393,421: PG2 / PG3 are replaced by zeros (model_multi.py:2406-2410)
     nvox = 40
     nvox_z = 40
     vmin = -2.5

@@ -582,6 +582,41 @@ def unproject_fuse_project(feats, Rcam, Kmat, config, proj_size, mode="sum", bn=
     return rays, fused
 
 
+def fusion_neck(feature_maps, Rcam, Kmat, config, params=None, levels=(2, 3, 4, 5, 6), proj_sizes=None):
+    """The fusion neck of ``MaskRCNN.build`` (model_multi.py:2382-2410): per pyramid level
+    ``unproj_feat -> grid_reas -> proj_grid -> depth_sampling``, the caller of every kernel of the path.
+
+    feature_maps: [P2..P6], each [B,V,fh,fw,C];  returns [PG2..PG6], each [B,P,P,C'] with P = IMAGE_SHAPE[0] / stride
+    (160/80/40/20/10 at 640).  ``params[name]`` holds the learnables of ``grid_reas_P<l>`` and ``grid_reas_depth_PG<l>``
+    (default: the ``weights`` registry).  With ``config.VANILLA`` false PG2 and PG3 are all-zero tensors (the reference
+    computes and then discards them, :2406-2410; they are not computed here).
+    GRID_REAS='add' takes the fused path: K1 (unproject + sum + BN + ReLU in registers) then K3b (projection + depth
+    collapse), two launches per level and neither the per-view grids nor the ray slices ever exist."""
+    params = params if params is not None else weights
+    ih = int(config.IMAGE_SHAPE[0])
+    outs = []
+    for i, (lvl, fm) in enumerate(zip(levels, feature_maps)):
+        fm = _cuda(fm, "P%d" % lvl)
+        P_ = int(proj_sizes[i]) if proj_sizes is not None else ih // (2 ** lvl)
+        B, Cc = fm.shape[0], fm.shape[-1]
+        if not getattr(config, "VANILLA", False) and lvl in (2, 3):
+            z = ih // (4 if lvl == 2 else 8)                        # :2407-2410 (both extents from IMAGE_SHAPE[0])
+            outs.append(torch.zeros((B, z, z, int(config.TOP_DOWN_PYRAMID_SIZE)), dtype=torch.float32, device=fm.device))
+            continue
+        gname, dname = "grid_reas_P%d" % lvl, "grid_reas_depth_PG%d" % lvl
+        gp, dp = params.get(gname, {}), params.get(dname)
+        if config.GRID_REAS == "add":
+            fused = unproject_fuse(fm, Rcam, Kmat, config, mode="sum", bn=gp.get("bn", _default_bn(Cc)), relu_out=True)
+            outs.append(proj_grid_depth_sampling([fused, Rcam, Kmat], config, P_, dname, params=dp))
+            continue
+        per_view = unproj_feat([fm, Rcam, Kmat], config)
+        fused = grid_reas(per_view, gname, config, params=gp)
+        del per_view
+        rays = proj_grid([fused, Rcam, Kmat], config, P_)
+        outs.append(depth_sampling(rays, config, dname, params=dp))
+    return outs
+
+
 # ------------------------------------------------------------------------------------------------
 class PyramidROIAlign:
     """``PyramidROIAlign(pool_shape)([boxes, image_meta] + feature_maps)`` (model_multi.py:779-885)."""

@@ -37,7 +37,7 @@ from .geometry import (tf1_range, tf1_linspace, matmul_seq, unproj_matrices,
 from .unproject import unproj_feat, unproj_feat_notebook, unproject_coords
 from .fusion import (grid_reas, fuse_views, batch_norm_affine, ident_fuse, convlstm,
                      convlstm_cell_step, channel_mean, unet_fuse, depth_sampling_conv3d,
-                     conv3d_strided_same, conv3d_transpose_same)
+                     conv3d_strided_same, conv3d_transpose_same, fusion_neck)
 from .projection import proj_grid, depth_sampling, project_indices
 from .roi_align import pyramid_roi_align, roi_levels, crop_and_resize
 from .detection import (apply_box_deltas, clip_boxes, iou_tf, non_max_suppression,

@@ -240,3 +240,26 @@ def grid_reas(grids, scope, cfg, params=None):
             h = h * bn[0] + bn[1]                               # :461
         return np.maximum(h, F32(0)).astype(F32)                # :462
     raise ValueError("GRID_REAS=%r is not on the hot path" % (mode,))
+
+
+def fusion_neck(feature_maps, Rcam, Kmat, cfg, params, levels=(2, 3, 4, 5, 6)):
+    """The fusion neck of ``MaskRCNN.build`` (model_multi.py:2382-2410): per level ``unproj_feat -> grid_reas -> proj_grid ->
+    depth_sampling``; PG2 / PG3 replaced by zeros when ``VANILLA`` is false (:2406-2410)."""
+    from .unproject import unproj_feat
+    from .projection import proj_grid, depth_sampling
+    ih = int(cfg.IMAGE_SHAPE[0])
+    outs = []
+    for lvl, fm in zip(levels, feature_maps):
+        B = fm.shape[0]
+        if not getattr(cfg, "VANILLA", False) and lvl in (2, 3):
+            z = ih // (4 if lvl == 2 else 8)
+            outs.append(np.zeros((B, z, z, int(cfg.TOP_DOWN_PYRAMID_SIZE)), F32))
+            continue
+        gp, dp = params.get("grid_reas_P%d" % lvl, {}), params["grid_reas_depth_PG%d" % lvl]
+        fused = grid_reas(unproj_feat(fm, Rcam, Kmat, cfg), "grid_reas_P%d" % lvl, cfg, gp)
+        rays = proj_grid(fused, Rcam, Kmat, cfg, ih // 2 ** lvl)
+        if cfg.GRID_REAS == "conv3d":
+            outs.append(depth_sampling_conv3d(rays, dp))
+        else:
+            outs.append(depth_sampling(rays, dp["weight"], dp.get("bias", 0.0), dp.get("bn")))
+    return outs

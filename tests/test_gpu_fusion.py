@@ -211,3 +211,45 @@ def test_errors():
     bad = small_cfg(nvox=16, vsize=0.1)      # tf.range would not give nvox centres
     with pytest.raises(ValueError):
         m.unproj_feat(d, bad)
+
+
+@pytest.mark.parametrize("mode,vanilla", [("add", True), ("add", False), ("ident", True), ("mean", True)])
+def test_fusion_neck_matches_oracle(mode, vanilla):
+    """MaskRCNN.build's fusion neck (model_multi.py:2382-2410): every level through unproj_feat -> grid_reas -> proj_grid ->
+    depth_sampling; 'add' runs the fused K1 + K3b pair."""
+    import mulit_view_object_detection_b200 as m
+    rng = np.random.default_rng(17)
+    B, V, C, S = 1, 3, 32, 5
+    cfg = small_cfg(GRID_REAS=mode, NUM_VIEWS=V, nvox=12, nvox_z=12, samples=S, TOP_DOWN_PYRAMID_SIZE=C,
+                    IMAGE_SHAPE=np.array([128, 128, 3]), VANILLA=vanilla)
+    levels = (2, 3, 4, 5, 6)
+    fmaps, Rcam, Kmat = [], None, None
+    for lvl in levels:
+        f, Rcam, Kmat = scene(cfg, B, V, 128 >> lvl, 128 >> lvl, C, seed=3, image_hw=(128, 128))
+        fmaps.append(f)
+    params = {}
+    for lvl in levels:
+        bn = (rng.uniform(0.8, 1.2, C).astype(np.float32), rng.normal(0, 0.05, C).astype(np.float32),
+              rng.normal(0, 0.05, C).astype(np.float32), rng.uniform(0.7, 1.3, C).astype(np.float32))
+        g = {"bn": bn}
+        if mode == "ident":
+            g.update(weight=(rng.standard_normal((V * C, C)) * 0.1).astype(np.float32), bias=rng.normal(0, 0.1, C).astype(np.float32))
+        if mode == "mean":
+            g = {}
+        params["grid_reas_P%d" % lvl] = g
+        params["grid_reas_depth_PG%d" % lvl] = {"weight": rng.normal(0.1, 0.3, S).astype(np.float32), "bias": 0.05,
+                                                "bn": (1.1, 0.02, -0.01, 0.9)}
+    dparams = {}
+    for k, v in params.items():                       # grid_reas learnables live on the device; depth / bn entries are host scalars
+        on_dev = k.startswith("grid_reas_P")
+        dparams[k] = {kk: (to_dev(vv)[0] if on_dev and kk in ("weight", "bias") else vv) for kk, vv in v.items()}
+    d = [to_dev(f)[0] for f in fmaps]
+    dR, dK = to_dev(Rcam, Kmat)
+    outs = m.fusion_neck(d, dR, dK, cfg, params=dparams)
+    refs = oracle.fusion_neck(fmaps, Rcam, Kmat, cfg, params)
+    assert len(outs) == 5
+    for lvl, o, r in zip(levels, outs, refs):
+        assert tuple(o.shape) == r.shape, lvl
+        close(o.cpu().numpy(), r, rtol=1e-5, atol=5e-6)
+    if not vanilla:
+        assert float(outs[0].abs().max()) == 0.0 and float(outs[1].abs().max()) == 0.0
