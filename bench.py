@@ -366,7 +366,8 @@ def run_cooperative(args):
         fn = lambda f, R, K, cfg_, P, mode: mvd.lstm_slab(f, R, K, cfg_, params, proj_size=P)
     else:
         fn = {"view_allreduce": mvd.view_shard_allreduce, "view_reduce_scatter": mvd.view_shard_reduce_scatter,
-              "slab_owner": mvd.slab_owner}[args.strategy]
+              "slab_owner": mvd.slab_owner,
+              "slab_owner_scatter": lambda *a, **k: mvd.slab_owner(*a, scatter_scenes=True, **k)}[args.strategy]
 
     def barrier():
         if world > 1:
@@ -418,7 +419,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-convlstm", action="store_true", help="skip the extra K2 (ConvLSTM on tensor cores) measurement")
-    ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner", "lstm_slab"],
+    ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner", "slab_owner_scatter", "lstm_slab"],
                     help="multi-GPU sharding: scene (default, weak scaling, no collective) or one of the cooperative "
                          "strategies of dist.py on a FIXED batch of --scenes scenes (strong scaling)")
     ap.add_argument("--nvox", type=int, default=64, help="voxels per grid axis (64 = workload T; 96 = config c5)")

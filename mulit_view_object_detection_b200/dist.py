@@ -160,15 +160,34 @@ def view_shard_reduce_scatter(feats, Rcam, Kmat, config, proj_size, mode="sum", 
     return rays, slab
 
 
-def slab_owner(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None):
+def _reduce_scatter_scenes(rays, group):
+    """Sum over ranks, each rank keeping the contiguous block of B/world scenes it owns (half the bytes of an all-reduce)."""
+    rank, ws = world(group)
+    if ws == 1:
+        return rays
+    B = rays.shape[0]
+    if B % ws:
+        raise ValueError("scatter_scenes needs the scene count (%d) divisible by the world size (%d)" % (B, ws))
+    nb = B // ws
+    if dist.get_backend(group) == "gloo":                # gloo has no reduce_scatter: reduce, then slice
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM, group=group)
+        return rays[rank * nb:(rank + 1) * nb].contiguous()
+    out = torch.empty((nb,) + tuple(rays.shape[1:]), dtype=rays.dtype, device=rays.device)
+    dist.reduce_scatter_tensor(out, rays.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def slab_owner(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None, scatter_scenes=False):
     """Owner-computes: every rank holds all views and fuses ALL of them for its own x-slab;
-    the only exchange is the all-reduce(sum) of the ray slices.  Returns (rays, grid slab)."""
+    the only exchange is the all-reduce(sum) of the ray slices -- or, with ``scatter_scenes``, a reduce-scatter that
+    leaves rank r with the ray slices of scenes [r*B/W, (r+1)*B/W) only (the downstream heads are data parallel over
+    scenes).  Returns (rays, grid slab)."""
     ops = ops or CudaOps()
     rank, ws = world(group)
     xb, xc = slab_bounds(config.nvox, rank, ws)
     slab = ops.unproject_fuse(feats, Rcam, Kmat, config, mode, x_slab=(xb, xc))
     rays = ops.proj_grid(slab, Rcam, Kmat, config, proj_size, x_slab=(xb, xc))
-    rays = _all_reduce(rays, dist.ReduceOp.SUM, group)
+    rays = _reduce_scatter_scenes(rays, group) if scatter_scenes else _all_reduce(rays, dist.ReduceOp.SUM, group)
     return rays, slab
 
 
