@@ -1,0 +1,103 @@
+"""GPU parity on hypothesis-drawn scenes: random shapes, ragged grids, arbitrary camera poses
+(including cameras inside / behind the grid, where the reference samples behind-camera points, Appendix B quirk 1) and
+random intrinsics.  Indices / masks / ray voxels / keep lists bit-exact, features and crops within 1e-5 relative."""
+import numpy as np
+import pytest
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+import oracle
+from helpers import small_cfg, to_dev, close
+
+pytestmark = pytest.mark.gpu
+SETTINGS = dict(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+
+
+def _m():
+    import mulit_view_object_detection_b200 as m
+    return m
+
+
+def _random_pose(rng, wild):
+    """camera->world [3,4]: a random rotation (small or arbitrary) and a translation near (or far from) the grid."""
+    a = rng.normal(0, 1.5 if wild else 0.2, 3)
+    th = np.linalg.norm(a) + 1e-12
+    k = a / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+    t = rng.normal(0, 3.0 if wild else 0.5, 3)
+    return np.concatenate([R, t[:, None]], axis=1).astype(np.float32)
+
+
+@st.composite
+def scenes(draw):
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    B, V = draw(st.integers(1, 2)), draw(st.integers(1, 5))
+    fh, fw = draw(st.integers(3, 24)), draw(st.integers(3, 24))
+    C = 4 * draw(st.integers(1, 20))
+    nvox, nvox_z = draw(st.integers(2, 14)), draw(st.integers(2, 18))
+    wild = draw(st.booleans())
+    cfg = small_cfg(nvox=nvox, nvox_z=nvox_z, NUM_VIEWS=V, samples=draw(st.integers(2, 9)), IMAGE_SHAPE=np.array([96, 96, 3]))
+    feats = rng.standard_normal((B, V, fh, fw, C)).astype(np.float32)
+    Rcam = np.stack([np.stack([_random_pose(rng, wild) for _ in range(V)]) for _ in range(B)])
+    f = rng.uniform(40, 160)
+    Kmat = np.broadcast_to(np.array([[f, 0, rng.uniform(30, 66)], [0, f * rng.uniform(0.8, 1.2), rng.uniform(30, 66)], [0, 0, 1]],
+                                    np.float32), (B, 3, 3)).copy()
+    return cfg, feats, Rcam, Kmat, draw(st.sampled_from(["sum", "mean", "max"])), draw(st.integers(2, 12))
+
+
+@settings(**SETTINGS)
+@given(scenes())
+def test_random_scenes_unproject_fuse_project(case):
+    m = _m()
+    cfg, feats, Rcam, Kmat, mode, P = case
+    d = to_dev(feats, Rcam, Kmat)
+    per_view, idx, valid = m.unproj_feat(d, cfg, return_aux=True)
+    o_views, o_idx, o_valid = oracle.unproj_feat(feats, Rcam, Kmat, cfg, return_aux=True)
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    assert np.array_equal(valid.cpu().numpy(), o_valid)
+    scale = max(1.0, float(np.abs(o_views).max()))
+    close(per_view.cpu().numpy(), o_views, rtol=1e-5, atol=1e-6 * scale)
+    rays, fused = m.unproject_fuse_project(*d, cfg, P, mode=mode)
+    o_fused = oracle.fuse_views(o_views, mode)
+    close(fused.cpu().numpy(), o_fused, rtol=1e-5, atol=2e-6 * scale)
+    _, vox, pvalid = m.proj_grid([fused, d[1], d[2]], cfg, P, return_aux=True)
+    o_vox, o_pvalid = oracle.project_indices(Rcam, Kmat, cfg, P)
+    assert np.array_equal(vox.cpu().numpy(), o_vox)
+    assert np.array_equal(pvalid.cpu().numpy().astype(bool), o_pvalid.astype(bool))
+    close(rays.cpu().numpy(), oracle.proj_grid(fused.cpu().numpy(), Rcam, Kmat, cfg, P), rtol=0, atol=0)   # a pure gather
+
+
+@settings(**SETTINGS)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 300), st.sampled_from([0.3, 0.5, 0.7]), st.integers(1, 50))
+def test_random_nms_keep_lists(seed, n, thr, max_out):
+    m = _m()
+    rng = np.random.default_rng(seed)
+    y1, x1 = rng.uniform(0, 0.8, n), rng.uniform(0, 0.8, n)
+    boxes = np.stack([y1, x1, y1 + rng.uniform(0.0, 0.3, n), x1 + rng.uniform(0.0, 0.3, n)], 1).astype(np.float32)
+    if n > 3:
+        boxes[1] = boxes[0]                      # exact duplicates and a degenerate (zero-area) box
+        boxes[2, 2:] = boxes[2, :2]
+    scores = rng.permutation(n).astype(np.float32) / n          # distinct
+    keep, count = m.non_max_suppression(*to_dev(boxes, scores), max_out, thr)
+    ref = oracle.non_max_suppression(boxes, scores, max_out, thr)
+    k = keep.cpu().numpy()
+    assert int(count) == ref.shape[0] and np.array_equal(k[:ref.shape[0]], ref) and np.all(k[ref.shape[0]:] == -1)
+
+
+@settings(**SETTINGS)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 40), st.sampled_from([(7, 7), (14, 14), (2, 5), (1, 1)]), st.integers(1, 6))
+def test_random_roi_align(seed, R, pool, c4):
+    m = _m()
+    rng = np.random.default_rng(seed)
+    C, B = 4 * c4, 2
+    maps = [rng.standard_normal((B, s, s + (i % 2), C)).astype(np.float32) for i, s in enumerate((24, 12, 6, 3))]
+    y1, x1 = rng.uniform(-0.1, 0.9, (B, R)), rng.uniform(-0.1, 0.9, (B, R))
+    boxes = np.stack([y1, x1, y1 + rng.uniform(0, 0.9, (B, R)), x1 + rng.uniform(0, 0.9, (B, R))], -1).astype(np.float32)
+    boxes[:, -1] = 0                                              # zero-padded proposal (level 2, quirk 13)
+    meta = np.tile(np.array([[0, 96, 96, 3, 96, 96, 3, 0, 0, 96, 96, 1.0] + [1] * 3], np.float32), (B, 1))
+    got, lv = m.PyramidROIAlign(pool)([to_dev(boxes)[0], meta] + to_dev(*maps), return_levels=True)
+    assert np.array_equal(lv.cpu().numpy(), oracle.roi_levels(boxes, (96, 96, 3)))
+    assert np.array_equal(got.cpu().numpy(), oracle.pyramid_roi_align(boxes, (96, 96, 3), maps, pool))     # bit-exact crops
