@@ -237,6 +237,61 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
             const float4* wslot = &sW[warp][sub * L];
             const uint4* oslot = &sO[warp][sub * L];
             float4 wn = wslot[0];                                      // weights travel one step ahead of their use
+            if (PLAIN) {
+                // Software pipeline over the run: the tap loads of step k+1 are issued BETWEEN the FMA groups of step k
+                // (a slot may be overwritten as soon as the FMAs that read it have been issued), so every reload has
+                // 8-16 FFMA2 of this warp's own work to hide behind instead of stalling the first FMA of its step.
+                // The per-accumulator FMA order (slots 00, 01, 10, 11) is unchanged.
+                auto reload_lo = [&](int kk, const uint4& o) {
+                    if (mlo & (1u << kk)) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) T00[c] = ldg2x2(vptr + coff(c) + o.x);
+                    }
+                    if (mlo & (1u << (L + kk))) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) T01[c] = ldg2x2(vptr + coff(c) + o.y);
+                    }
+                };
+                auto reload_hi = [&](int kk, const uint4& o) {
+                    if (mhi & (1u << kk)) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) T10[c] = ldg2x2(vptr + coff(c) + o.z);
+                    }
+                    if (mhi & (1u << (L + kk))) {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) T11[c] = ldg2x2(vptr + coff(c) + o.w);
+                    }
+                };
+                if (many & (1u | (1u << L))) {                          // step 0: nothing of this run to hide behind
+                    const uint4 o = oslot[0];
+                    reload_lo(0, o); reload_hi(0, o);
+                }
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    const bool valid = (vm >> k) & 1u;                      // warp-uniform
+                    const float4 ww = wn;
+                    if (k + 1 < L) wn = wslot[k + 1];                       // broadcast LDS.128
+                    const bool nxt = (k + 1 < L) && (many & ((1u << (k + 1)) | (1u << (L + k + 1))));   // step k+1 reloads something
+                    if (!valid) {
+                        if (nxt) { const uint4 o = oslot[k + 1]; reload_lo(k + 1, o); reload_hi(k + 1, o); }
+                        continue;
+                    }
+                    if (nxt) {
+                        const uint4 o = oslot[k + 1];                       // broadcast LDS.128
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) acc[k][c] = fma2x2(ww.y, T01[c], fma2x2(ww.x, T00[c], acc[k][c]));
+                        reload_lo(k + 1, o);
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) acc[k][c] = fma2x2(ww.w, T11[c], fma2x2(ww.z, T10[c], acc[k][c]));
+                        reload_hi(k + 1, o);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c)                          // 8 FFMA2 = 16 fp32 FMAs
+                            acc[k][c] = fma2x2(ww.w, T11[c], fma2x2(ww.z, T10[c], fma2x2(ww.y, T01[c], fma2x2(ww.x, T00[c], acc[k][c]))));
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int k = 0; k < L; ++k) {
                 const bool valid = (vm >> k) & 1u;                          // warp-uniform
