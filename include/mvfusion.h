@@ -94,6 +94,11 @@ int mvf_unproject_fuse(const float* feats, const float* Rcam, const float* Rmain
 int mvf_view_reduce(const float* in, int B, int V, long long N, int C, int mode, int flags,
                     const float* bn_scale, const float* bn_shift, float* out, void* stream);
 
+/* ---- notebook grid_reas 'mean' ---------------------------------------------------------------
+ * replaces Notebook/projection.py:526-529,549: the mean is taken over the CHANNEL axis and the V per-view scalars
+ * become the channels, then ReLU.  in [B,V,N,C] -> out [B,N,V]. */
+int mvf_channel_mean(const float* in, int B, int V, long long N, int C, float* out, void* stream);
+
 /* ---- grid_reas 'ident' -----------------------------------------------------------------------
  * replaces model_multi.py:443-455: ReLU -> concat views on channels (v*C+c) -> Conv3D 1x1x1
  * (+bias) -> BN -> ReLU.   in [B,V,N,C], weight [V*C,Cout], bias [Cout] -> out [B,N,Cout]. */

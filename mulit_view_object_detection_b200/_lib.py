@@ -48,6 +48,7 @@ _SIGS = {
     "mvf_unproject_fuse": (_i, [_p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i,
                                 _p, _p, _p, _p, _p, _p, _p]),
     "mvf_view_reduce": (_i, [_p, _i, _i, _ll, _i, _i, _i, _p, _p, _p, _p]),
+    "mvf_channel_mean": (_i, [_p, _i, _i, _ll, _i, _p, _p]),
     "mvf_ident_fuse": (_i, [_p, _p, _p, _p, _p, _i, _i, _ll, _i, _i, _p, _p]),
     "mvf_conv3d_wsplit_bytes": (_sz, [_i, _i, _i, _i]),
     "mvf_conv3d_prepare": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),

@@ -185,9 +185,41 @@ convlstm_step_kernel(const float* __restrict__ x, const float* __restrict__ h_pr
     }
 }
 
+// Notebook GRID_REAS='mean' (Notebook/projection.py:526-529,549): mean over the CHANNEL axis, the V per-view scalars become the
+// channels, ReLU.  One warp per (b, v, n) channel vector: lanes stride over float4s, xor-shuffle tree.
+__global__ void __launch_bounds__(256)
+channel_mean_kernel(const float4* __restrict__ in, float* __restrict__ out, int V, long long N, int C4, long long rows) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);          // row = (b * V + v) * N + n
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int c = lane; c < C4; c += 32) {
+        const float4 v = __ldg(in + row * C4 + c);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) {
+        const long long n = row % N, bv = row / N;
+        const long long b = bv / V, v = bv % V;
+        out[(b * N + n) * V + v] = fmaxf(s / (float)(4 * C4), 0.f);
+    }
+}
+
 }  // namespace mvf
 
 using namespace mvf;
+
+extern "C" int mvf_channel_mean(const float* in, int B, int V, long long N, int C, float* out, void* stream) {
+    if (!in || !out) return MVF_ENULL;
+    if (B <= 0 || V <= 0 || N <= 0 || C <= 0) return MVF_EINVAL;
+    if (C % 4 != 0 || !aligned16(in)) return MVF_EALIGN;
+    const long long rows = (long long)B * V * N;
+    if ((rows + 7) / 8 > 2147483647ll) return MVF_EUNSUPPORTED;
+    channel_mean_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>((const float4*)in, out, V, N, C / 4, rows);
+    count_launch();
+    return check_launch();
+}
 
 extern "C" int mvf_view_reduce(const float* in, int B, int V, long long N, int C, int mode, int flags,
                                const float* bn_scale, const float* bn_shift, float* out, void* stream) {

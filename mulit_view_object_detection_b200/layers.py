@@ -165,6 +165,16 @@ def view_reduce(x, mode, bn=None, relu_in=False, relu_out=False):
     return out
 
 
+def channel_mean(x):
+    """The notebook's ``GRID_REAS='mean'`` (Notebook/projection.py:526-529,549): mean over the CHANNEL axis, the V per-view
+    scalars become the channels, ReLU.  [B,V,X,Y,Z,C] -> [B,X,Y,Z,V]."""
+    x = _cuda(x, "inputs")
+    B, V, X, Y, Z, Cc = x.shape
+    out = torch.empty((B, X, Y, Z, V), dtype=torch.float32, device=x.device)
+    check(lib.mvf_channel_mean(_ptr(x), B, V, X * Y * Z, Cc, _ptr(out), _stream()), "mvf_channel_mean")
+    return out
+
+
 def convlstm_step(x, h_prev, c_prev, W, bias, forget_bias=1.0, relu_in=False):
     """One ``ConvLSTMCell.call`` (mrcnn/recurrent.py:442-479): returns (h, c)."""
     x = _cuda(x, "x")

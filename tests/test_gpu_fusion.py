@@ -253,3 +253,15 @@ def test_fusion_neck_matches_oracle(mode, vanilla):
         close(o.cpu().numpy(), r, rtol=1e-5, atol=5e-6)
     if not vanilla:
         assert float(outs[0].abs().max()) == 0.0 and float(outs[1].abs().max()) == 0.0
+
+
+def test_notebook_channel_mean():
+    """Notebook GRID_REAS='mean' (Notebook/projection.py:526-529,549): mean over channels, views become channels, ReLU."""
+    import mulit_view_object_detection_b200 as m
+    rng = np.random.default_rng(2)
+    for shape in ((2, 3, 4, 5, 6, 64), (1, 5, 3, 3, 3, 4), (1, 2, 2, 2, 2, 260)):
+        g = rng.standard_normal(shape).astype(np.float32)
+        out = m.channel_mean(to_dev(g)[0])
+        ref = oracle.channel_mean(g)
+        assert tuple(out.shape) == ref.shape
+        close(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
