@@ -120,6 +120,8 @@ int mvf_ident_fuse(const float* in, const float* weight, const float* bias,
  * Weights: mvf_conv3d_prepare(W) once per tensor.  W is the Keras kernel: Conv3D [k,k,k,Cin,Cout], Conv3DTranspose
  *     [3,3,3,Cout,Cin]; Cin = V*C + C2.  chan_interleave = S > 1: the reference orders the input channels (c*S + s)
  *     while `in` supplies S sources of C channels (depth_sampling, :468-470).
+ * ws: mvf_conv3d_tc_workspace_bytes(...) bytes of device scratch for the hi/lo halves of the activations -- 0 (ws may be
+ *     NULL) when the split is fused into the GEMM, which the library chooses for large 1x1x1 convolutions.
  * Needs C % 32 == 0, C2 % 32 == 0, Cout % 16 == 0 (MVF_EUNSUPPORTED otherwise). */
 #define MVF_CONV_S1   0
 #define MVF_CONV_S2   1
@@ -127,7 +129,7 @@ int mvf_ident_fuse(const float* in, const float* weight, const float* bias,
 size_t mvf_conv3d_wsplit_bytes(int kind, int ksize, int Cin, int Cout);
 int mvf_conv3d_prepare(const float* W, int kind, int ksize, int Cin, int Cout, int chan_interleave,
                        float* wsplit, void* stream);
-size_t mvf_conv3d_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C, int C2);
+size_t mvf_conv3d_tc_workspace_bytes(int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout);
 int mvf_conv3d_tc(const float* in, const float* in2, const float* wsplit, const float* bias,
                   const float* bn_scale, const float* bn_shift, const float* pre_scale, const float* pre_shift,
                   int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout, int flags,
@@ -137,10 +139,10 @@ int mvf_conv3d_tc(const float* in, const float* in2, const float* wsplit, const 
  * Same contract as mvf_ident_fuse (model_multi.py:443-455) for C % 32 == 0 and Cout % 16 == 0
  * (MVF_EUNSUPPORTED otherwise: use mvf_ident_fuse); the grid shape is passed as X,Y,Z (N = X*Y*Z).
  *   mvf_ident_prepare(weight [V*C,Cout]) -> wsplit (mvf_ident_wsplit_bytes): K-major hi/lo halves, once per weight.
- * ws: mvf_ident_tc_workspace_bytes(...) bytes of device scratch (hi/lo halves of relu(in)). */
+ * ws: mvf_ident_tc_workspace_bytes(...) bytes of device scratch (hi/lo halves of relu(in); 0 when the split is fused). */
 size_t mvf_ident_wsplit_bytes(int V, int C, int Cout);
 int mvf_ident_prepare(const float* weight, int V, int C, int Cout, float* wsplit, void* stream);
-size_t mvf_ident_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C);
+size_t mvf_ident_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C, int Cout);
 int mvf_ident_fuse_tc(const float* in, const float* wsplit, const float* bias,
                       const float* bn_scale, const float* bn_shift,
                       int B, int V, int X, int Y, int Z, int C, int Cout,

@@ -38,6 +38,7 @@ constexpr uint32_t TC_A_BYTES = TC_M * TC_K * 4;             // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_N * TC_K * 4;             // 32 KB
 constexpr uint32_t TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;
 constexpr uint32_t TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TC_CONV_WARPS = 2;                            // warps 2-3 convert raw tiles into hi/lo halves
 
 struct TcArgs {
     const float* bias; const float* c_prev; float* h_out; float* c_out;
@@ -49,6 +50,9 @@ struct TcArgs {
     int V, Cout;                  // view-sources of x, output channels
     int kind, ksize;              // MVF_CONV_S1 / _S2 / MVF_DECONV_S2, kernel size per axis (1 or 3)
     int relu_out;
+    // fused operand split: the TMA loads the RAW fp32 activation tile and warps 2-3 turn it into (hi, lo) in shared memory
+    int fused_split, relu_x, relu_h;
+    const float* pre_scale; const float* pre_shift;
     const float* bn_scale; const float* bn_shift; float* out;
     int promote;                  // K-chunks per promotion of the partial accumulator into the master (0 = never)
     float forget_bias;
@@ -164,6 +168,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
     const uint32_t part_full = bar_base + 8u * (2 * TC_STAGES);                    // MMA -> epilogue: a partial accumulator is complete
     const uint32_t part_empty = bar_base + 8u * (2 * TC_STAGES + 1);               // epilogue -> MMA: it has been added into the master
     const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 2);                // the allocator writes the TMEM base address here
+    auto conv_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 3 + s); };  // converter warps -> MMA: hi/lo halves are in place
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // tile coordinates: blockIdx.x -> (b, tx, ty, tz) box of BX x BY x BZ voxels, blockIdx.y -> 64-filter group
@@ -175,7 +180,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
     const int ntile = blockIdx.y;
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(conv_bar(s), TC_CONV_WARPS); }
         mbar_init(part_full, 1); mbar_init(part_empty, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -198,35 +203,82 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
     const int gsz = a.promote > 0 ? a.promote : nchunks;         // K-chunks per partial accumulation chain
     const int ngroups = (nchunks + gsz - 1) / gsz;
 
+    // K-chunk `it` -> source (x view v / h), channel offset, tap shift, weight row, batch slice of the TMA tensor
+    struct Chunk { int dx, dy, dz, c0, krow, bidx, v; bool from_h; };
+    auto decode_chunk = [&](int it) {
+        Chunk q = {0, 0, 0, 0, 0, b, 0, false};
+        if (IDENT) {                                     // tap-major; inside a tap: view 0 chunks, ..., view V-1 chunks, h chunks
+            const int tap = it / per_tap, kc = it - tap * per_tap;
+            const TapRef r = decode_tap(a.kind, a.ksize, cls, tap);
+            q.dx = r.dx; q.dy = r.dy; q.dz = r.dz;
+            q.from_h = kc >= a.V * cx;
+            if (q.from_h) { q.c0 = (kc - a.V * cx) * TC_K; q.krow = r.kidx * CF + a.V * a.C + q.c0; q.bidx = b * nsub + r.sub; }
+            else { q.v = kc / cx; q.c0 = (kc - q.v * cx) * TC_K; q.krow = r.kidx * CF + q.v * a.C + q.c0; q.bidx = (b * a.V + q.v) * nsub + r.sub; }
+        } else {
+            const int tap = it / per_tap, kc = it - tap * per_tap;
+            q.dx = tap / 9 - 1; q.dy = (tap / 3) % 3 - 1; q.dz = tap % 3 - 1;           // W[kx][ky][kz], SAME padding
+            q.from_h = kc >= cx;
+            q.c0 = (q.from_h ? kc - cx : kc) * TC_K;
+            q.krow = tap * CF + (q.from_h ? a.C : 0) + q.c0;                            // row of the K-major weight matrix
+        }
+        return q;
+    };
+
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         for (int it = 0; it < nchunks; ++it) {
             const int s = it % TC_STAGES;
             const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
             mbar_wait(empty_bar(s), phase ^ 1u);
-            int dx = 0, dy = 0, dz = 0, c0, krow, bidx = b;
-            bool from_h = false;
-            if (IDENT) {                                     // tap-major; inside a tap: view 0 chunks, ..., view V-1 chunks, h chunks
-                const int tap = it / per_tap, kc = it - tap * per_tap;
-                const TapRef r = decode_tap(a.kind, a.ksize, cls, tap);
-                dx = r.dx; dy = r.dy; dz = r.dz;
-                from_h = kc >= a.V * cx;
-                if (from_h) { c0 = (kc - a.V * cx) * TC_K; krow = r.kidx * CF + a.V * a.C + c0; bidx = b * nsub + r.sub; }
-                else { const int v = kc / cx; c0 = (kc - v * cx) * TC_K; krow = r.kidx * CF + v * a.C + c0; bidx = (b * a.V + v) * nsub + r.sub; }
-            } else {
-                const int tap = it / per_tap, kc = it - tap * per_tap;
-                dx = tap / 9 - 1; dy = (tap / 3) % 3 - 1; dz = tap % 3 - 1;             // W[kx][ky][kz], SAME padding
-                from_h = kc >= cx;
-                c0 = (from_h ? kc - cx : kc) * TC_K;
-                krow = tap * CF + (from_h ? a.C : 0) + c0;                              // row of the K-major weight matrix
-            }
+            const Chunk q = decode_chunk(it);
             const uint32_t st = smem_base + s * TC_STAGE_BYTES;
-            mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
-            const int xin = x0 + dx + a.halo_lo;                      // halo planes hold the neighbour slab's data; past them the TMA
-            tma_load_5d(st, from_h ? &tm_hh : &tm_xh, full_bar(s), c0, z0 + dz, y0 + dy, xin, bidx);      // zero fill is the grid border
-            tma_load_5d(st + TC_A_BYTES, from_h ? &tm_hl : &tm_xl, full_bar(s), c0, z0 + dz, y0 + dy, xin, bidx);
-            tma_load_2d(st + 2 * TC_A_BYTES, &tm_wh, full_bar(s), krow, ntile * TC_N);
-            tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tm_wl, full_bar(s), krow, ntile * TC_N);
+            const int xin = x0 + q.dx + a.halo_lo;                    // halo planes hold the neighbour slab's data; past them the TMA
+            if (a.fused_split) {                                      // zero fill is the grid border
+                mbar_expect_tx(full_bar(s), TC_A_BYTES + 2 * TC_B_BYTES);
+                tma_load_5d(st, q.from_h ? &tm_hh : &tm_xh, full_bar(s), q.c0, z0 + q.dz, y0 + q.dy, xin, q.bidx);      // raw fp32 tile
+            } else {
+                mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
+                tma_load_5d(st, q.from_h ? &tm_hh : &tm_xh, full_bar(s), q.c0, z0 + q.dz, y0 + q.dy, xin, q.bidx);
+                tma_load_5d(st + TC_A_BYTES, q.from_h ? &tm_hl : &tm_xl, full_bar(s), q.c0, z0 + q.dz, y0 + q.dy, xin, q.bidx);
+            }
+            tma_load_2d(st + 2 * TC_A_BYTES, &tm_wh, full_bar(s), q.krow, ntile * TC_N);
+            tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tm_wl, full_bar(s), q.krow, ntile * TC_N);
+        }
+    } else if ((warp == 2 || warp == 3) && a.fused_split) {
+        // ===== operand converter: raw fp32 tile -> a_hi (in place) and a_lo, with the ReLU / depthwise affine in front of the conv.
+        // The 128-byte swizzle only permutes 16-byte chunks inside a row, so the split is position-wise; the channel of a chunk
+        // (needed for the per-channel affine) is (chunk ^ (row & 7)) * 4.
+        const int ct = (warp - 2) * 32 + lane;
+        for (int it = 0; it < nchunks; ++it) {
+            const int s = it % TC_STAGES;
+            const uint32_t phase = (uint32_t)(it / TC_STAGES) & 1u;
+            const Chunk q = decode_chunk(it);
+            const bool relu = q.from_h ? a.relu_h != 0 : a.relu_x != 0;
+            const bool affine = a.pre_scale != nullptr && !q.from_h;
+            const int chbase = q.v * a.C + q.c0;
+            mbar_wait(full_bar(s), phase);
+            const uint32_t st = smem_base + s * TC_STAGE_BYTES;
+#pragma unroll 4
+            for (int i = ct; i < (int)(TC_A_BYTES / 16); i += TC_CONV_WARPS * 32) {
+                float4 v;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(st + 16u * i));
+                if (affine) {
+                    const int ch = chbase + (((i & 7) ^ ((i >> 3) & 7)) << 2);
+                    const float4 sc = ldg4(a.pre_scale + ch), sh = ldg4(a.pre_shift + ch);
+                    v = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+                }
+                if (relu) v = relu4(v);
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(st + 16u * i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(st + TC_A_BYTES + 16u * i), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's async reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(conv_bar(s));
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer: D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (3xTF32) =====
@@ -238,7 +290,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
                 mbar_wait(part_empty, (uint32_t)(grp - 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            mbar_wait(full_bar(s), phase);
+            mbar_wait(a.fused_split ? conv_bar(s) : full_bar(s), phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t st = smem_base + s * TC_STAGE_BYTES;
             const uint64_t dah = umma_desc_sw128(st), dal = umma_desc_sw128(st + TC_A_BYTES);
@@ -509,29 +561,36 @@ extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, co
                                          const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
                                          int halo_lo, int halo_hi, int flags, float* h_out, float* c_out,
                                          void* ws, size_t ws_bytes, void* stream) {
-    if (!x || !wsplit || !bias || !h_out || !c_out || !ws) return MVF_ENULL;
+    if (!x || !wsplit || !bias || !h_out || !c_out) return MVF_ENULL;
     if (B <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || F <= 0) return MVF_EINVAL;
     if (halo_lo < 0 || halo_lo > 1 || halo_hi < 0 || halo_hi > 1) return MVF_EINVAL;
     const int Xin = X + halo_lo + halo_hi;
     if ((h_prev == nullptr) != (c_prev == nullptr)) return MVF_ENULL;
     if (h_out == h_prev || c_out == h_prev) return MVF_EINVAL;
     if (C % TC_K != 0 || F % TC_FPT != 0) return MVF_EUNSUPPORTED;
-    if (!aligned16(x) || !aligned16(wsplit) || !aligned16(ws) || !aligned16(h_out) || !aligned16(c_out) ||
+    if (!aligned16(x) || !aligned16(wsplit) || (ws && !aligned16(ws)) || !aligned16(h_out) || !aligned16(c_out) ||
         (h_prev && (!aligned16(h_prev) || !aligned16(c_prev)))) return MVF_EALIGN;
-    if (ws_bytes < mvf_convlstm_tc_workspace_bytes(B, Xin, Y, Z, C, F)) return MVF_EWORKSPACE;
+    // The hi/lo halves of x and h are produced by a separate elementwise pass: every element is read 27 x 4F/256 times by the
+    // GEMM, so the pass costs 1 % while converting inside the 2-stage ring costs 10 % (measured: 35.7 vs 32.3 ms at c3 size).
+    // MVF_TC_FUSED_SPLIT=1 selects the in-kernel converter for A/B measurement.
+    static const bool split_pass = [] { const char* e = getenv("MVF_TC_FUSED_SPLIT"); return !(e && atoi(e) != 0); }();
+    if (split_pass && (!ws || ws_bytes < mvf_convlstm_tc_workspace_bytes(B, Xin, Y, Z, C, F))) return MVF_EWORKSPACE;
     if (!encode_tiled()) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
     const long long vox = (long long)B * Xin * Y * Z;
-    float* xh = (float*)ws; float* xl = xh + vox * C; float* hh = xl + vox * C; float* hl = hh + vox * F;
-    {
+    const float *xh = x, *xl = x, *hh = h_prev ? h_prev : x, *hl = hh;
+    if (split_pass) {
+        float* w0 = (float*)ws;
+        float* w1 = w0 + vox * C; float* w2 = w1 + vox * C; float* w3 = w2 + vox * F;
         const long long n4 = vox * C / 4;
-        tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)x, (float4*)xh, (float4*)xl, n4, (flags & MVF_FLAG_RELU_IN) != 0);
+        tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)x, (float4*)w0, (float4*)w1, n4, (flags & MVF_FLAG_RELU_IN) != 0);
         count_launch();
-    }
-    if (h_prev) {
-        const long long n4 = vox * F / 4;
-        tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)h_prev, (float4*)hh, (float4*)hl, n4, 0);
-        count_launch();
+        if (h_prev) {
+            const long long m4 = vox * F / 4;
+            tf32_split_kernel<<<(unsigned)((m4 + 255) / 256), 256, 0, s>>>((const float4*)h_prev, (float4*)w2, (float4*)w3, m4, 0);
+            count_launch();
+        }
+        xh = w0; xl = w1; hh = w2; hl = w3;
     }
     TcArgs a;
     a.bias = bias; a.c_prev = c_prev; a.h_out = h_out; a.c_out = c_out;
@@ -542,6 +601,7 @@ extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, co
     a.tiles_z = (Z + a.BZ - 1) / a.BZ; a.tiles_y = (Y + a.BY - 1) / a.BY; a.tiles_x = (X + a.BX - 1) / a.BX;
     a.has_h = h_prev != nullptr; a.forget_bias = forget_bias;
     a.halo_lo = halo_lo; a.halo_hi = halo_hi;
+    a.fused_split = !split_pass; a.relu_x = (flags & MVF_FLAG_RELU_IN) != 0; a.relu_h = 0; a.pre_scale = nullptr; a.pre_shift = nullptr;
     a.V = 1; a.Cout = 0; a.kind = 0; a.ksize = 3; a.relu_out = 0; a.bn_scale = nullptr; a.bn_shift = nullptr; a.out = nullptr;
     // K-chunks (of 32) per partial accumulation chain; MVF_TC_PROMOTE overrides (0 = one long chain, for A/B measurement)
     static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
@@ -597,16 +657,33 @@ extern "C" int mvf_conv3d_prepare(const float* W, int kind, int ksize, int Cin, 
     return check_launch();
 }
 
-extern "C" size_t mvf_conv3d_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C, int C2) {
-    if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || C2 < 0) return 0;
-    return (size_t)2 * B * X * Y * Z * ((size_t)V * C + C2) * sizeof(float);      // hi and lo halves of both sources
+// Where the activation split happens.  A separate elementwise pass (workspace = hi and lo halves of both sources) is the
+// default: with k=3 every element is read 27 times by the GEMM, and small problems are latency-bound chains that the extra
+// converter stage lengthens.  The 1x1x1 members at scale read every activation exactly once and are HBM-bound, so they convert
+// inside the GEMM (warps 2-3) and touch no workspace: 'ident' 2048->256 at 64^3 1.67 ms instead of 2.60.
+// MVF_TC_SPLIT_PASS=1 / MVF_TC_FUSED_SPLIT=1 force either choice (the stride-2 conv always needs the pass: it re-lays the operand).
+static bool conv3d_fused_split(int kind, int ksize, int B, int X, int Y, int Z, int Cout) {
+    static const int force = [] {
+        const char* p = getenv("MVF_TC_SPLIT_PASS"); const char* f = getenv("MVF_TC_FUSED_SPLIT");
+        return (p && atoi(p) != 0) ? 1 : (f && atoi(f) != 0) ? 2 : 0;
+    }();
+    if (kind == MVF_CONV_S2 || force == 1) return false;
+    if (force == 2) return true;
+    const long long tiles = (((long long)B * X * Y * Z + TC_M - 1) / TC_M) * ((Cout + TC_N - 1) / TC_N);
+    return kind == MVF_CONV_S1 && ksize == 1 && tiles >= 2 * 148;
+}
+
+extern "C" size_t mvf_conv3d_tc_workspace_bytes(int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout) {
+    if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || C2 < 0 || Cout <= 0) return 0;
+    if (conv3d_fused_split(kind, ksize, B, X, Y, Z, Cout)) return 0;
+    return (size_t)2 * B * X * Y * Z * ((size_t)V * C + C2) * sizeof(float);
 }
 
 extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsplit, const float* bias,
                              const float* bn_scale, const float* bn_shift, const float* pre_scale, const float* pre_shift,
                              int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout, int flags,
                              float* out, void* ws, size_t ws_bytes, void* stream) {
-    if (!in || !wsplit || !bias || !out || !ws) return MVF_ENULL;
+    if (!in || !wsplit || !bias || !out) return MVF_ENULL;
     if ((bn_scale == nullptr) != (bn_shift == nullptr) || (pre_scale == nullptr) != (pre_shift == nullptr)) return MVF_ENULL;
     if ((in2 == nullptr) != (C2 == 0)) return MVF_EINVAL;
     if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || C2 < 0 || Cout <= 0) return MVF_EINVAL;
@@ -614,21 +691,27 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     if (C % TC_K != 0 || C2 % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
     if (kind == MVF_CONV_S2 && ((X | Y | Z) & 1)) return MVF_EUNSUPPORTED;      // odd sizes pad on both sides in TF; not built
     if (pre_scale && in2) return MVF_EUNSUPPORTED;
-    if (!aligned16(in) || !aligned16(wsplit) || !aligned16(ws) || !aligned16(out) || (in2 && !aligned16(in2)) ||
+    if (!aligned16(in) || !aligned16(wsplit) || (ws && !aligned16(ws)) || !aligned16(out) || (in2 && !aligned16(in2)) ||
         (pre_scale && (!aligned16(pre_scale) || !aligned16(pre_shift)))) return MVF_EALIGN;
-    if (ws_bytes < mvf_conv3d_tc_workspace_bytes(B, V, X, Y, Z, C, C2)) return MVF_EWORKSPACE;
+    if (pre_scale && ksize != 1) return MVF_EUNSUPPORTED;                       // the affine must not touch the SAME padding
+    const int relu_in = (flags & MVF_FLAG_RELU_IN) != 0, s2d = kind == MVF_CONV_S2;
+    const bool split_pass = !conv3d_fused_split(kind, ksize, B, X, Y, Z, Cout);
+    if (split_pass && (!ws || ws_bytes < mvf_conv3d_tc_workspace_bytes(kind, ksize, B, V, X, Y, Z, C, C2, Cout))) return MVF_EWORKSPACE;
     if (!encode_tiled()) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
-    const int relu_in = (flags & MVF_FLAG_RELU_IN) != 0, s2d = kind == MVF_CONV_S2;
     const long long n1 = (long long)B * V * X * Y * Z * C, n2 = (long long)B * X * Y * Z * C2;
-    float* xh = (float*)ws; float* xl = xh + n1; float* hh = xl + n1; float* hl = hh + n2;
-    act_split_kernel<<<(unsigned)((n1 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)xh, (float4*)xl, n1 / 4, X, Y, Z, C / 4, V,
-                                                                    relu_in, s2d, (const float4*)pre_scale, (const float4*)pre_shift);
-    count_launch();
-    if (in2) {
-        act_split_kernel<<<(unsigned)((n2 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in2, (float4*)hh, (float4*)hl, n2 / 4, X, Y, Z, C2 / 4, 1,
-                                                                        relu_in, s2d, nullptr, nullptr);
+    const float *xh = in, *xl = in, *hh = in2, *hl = in2;
+    if (split_pass) {
+        float* w0 = (float*)ws; float* w1 = w0 + n1; float* w2 = w1 + n1; float* w3 = w2 + n2;
+        act_split_kernel<<<(unsigned)((n1 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)w0, (float4*)w1, n1 / 4, X, Y, Z, C / 4, V,
+                                                                        relu_in, s2d, (const float4*)pre_scale, (const float4*)pre_shift);
         count_launch();
+        if (in2) {
+            act_split_kernel<<<(unsigned)((n2 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in2, (float4*)w2, (float4*)w3, n2 / 4, X, Y, Z, C2 / 4, 1,
+                                                                            relu_in, s2d, nullptr, nullptr);
+            count_launch();
+        }
+        xh = w0; xl = w1; hh = w2; hl = w3;
     }
     // M space: the output lattice for a conv, the INPUT lattice for the transposed conv; a 1x1x1 conv has no neighbourhood,
     // so its voxels are flattened into one axis (full 128-row tiles whatever the grid shape)
@@ -647,6 +730,7 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     a.BX = TC_M / (a.BZ * a.BY);
     a.tiles_z = (MZ + a.BZ - 1) / a.BZ; a.tiles_y = (MY + a.BY - 1) / a.BY; a.tiles_x = (MX + a.BX - 1) / a.BX;
     a.has_h = in2 != nullptr; a.forget_bias = 0.f; a.halo_lo = 0; a.halo_hi = 0;
+    a.fused_split = !split_pass; a.relu_x = relu_in; a.relu_h = relu_in; a.pre_scale = pre_scale; a.pre_shift = pre_shift;
     a.V = V; a.Cout = Cout; a.kind = kind; a.ksize = ksize; a.relu_out = (flags & MVF_FLAG_RELU_OUT) != 0;
     a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.out = out;
     static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
@@ -682,7 +766,9 @@ extern "C" int mvf_ident_prepare(const float* weight, int V, int C, int Cout, fl
     if (C % TC_K != 0) return MVF_EUNSUPPORTED;
     return mvf_conv3d_prepare(weight, MVF_CONV_S1, 1, V * C, Cout, 0, wsplit, stream);
 }
-extern "C" size_t mvf_ident_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C) { return mvf_conv3d_tc_workspace_bytes(B, V, X, Y, Z, C, 0); }
+extern "C" size_t mvf_ident_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C, int Cout) {
+    return mvf_conv3d_tc_workspace_bytes(MVF_CONV_S1, 1, B, V, X, Y, Z, C, 0, Cout);
+}
 extern "C" int mvf_ident_fuse_tc(const float* in, const float* wsplit, const float* bias,
                                  const float* bn_scale, const float* bn_shift,
                                  int B, int V, int X, int Y, int Z, int C, int Cout,

@@ -27,6 +27,7 @@ use the Keras initial values (BatchNorm gamma=1, beta=0, mean=0, var=1).
 import ctypes as C
 
 import numpy as np
+import os
 import torch
 
 from . import _lib
@@ -224,7 +225,7 @@ class ConvLSTMTensorCore:
         if Cc != self.C:
             raise ValueError("x has %d channels, the weights expect %d" % (Cc, self.C))
         need = lib.mvf_convlstm_tc_workspace_bytes(B, X, Y, Z, self.C, self.F)
-        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device:
+        if need and (self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device):
             self._ws = torch.empty(need // 4, dtype=torch.float32, device=x.device)
         h = torch.empty((B, X, Y, Z, self.F), dtype=torch.float32, device=x.device)
         c = torch.empty_like(h)
@@ -232,7 +233,7 @@ class ConvLSTMTensorCore:
         cp = _cuda(c_prev, "c_prev") if c_prev is not None else None
         rc = lib.mvf_convlstm_step_tc(_ptr(x), _ptr(hp), _ptr(cp), _ptr(self.wsplit), _ptr(self.bias), self.forget_bias,
                                       B, X, Y, Z, self.C, self.F, _lib.FLAG_RELU_IN if relu_in else 0,
-                                      _ptr(h), _ptr(c), _ptr(self._ws), self._ws.numel() * 4, _stream())
+                                      _ptr(h), _ptr(c), _ptr(self._ws) if need else None, self._ws.numel() * 4 if need else 0, _stream())
         check(rc, "mvf_convlstm_step_tc")
         return h, c
 
@@ -248,7 +249,7 @@ class ConvLSTMTensorCore:
         if Cc != self.C or Xs <= 0:
             raise ValueError("bad slab: x %s, halo %s, C %d" % (tuple(x.shape), (lo, hi), self.C))
         need = lib.mvf_convlstm_tc_workspace_bytes(B, Xin, Y, Z, self.C, self.F)
-        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device:
+        if need and (self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device):
             self._ws = torch.empty(need // 4, dtype=torch.float32, device=x.device)
         h = h_out if h_out is not None else torch.zeros((B, Xin, Y, Z, self.F), dtype=torch.float32, device=x.device)
         c = torch.empty((B, Xs, Y, Z, self.F), dtype=torch.float32, device=x.device)
@@ -256,7 +257,7 @@ class ConvLSTMTensorCore:
         cp = _cuda(c_prev, "c_prev") if c_prev is not None else None
         rc = lib.mvf_convlstm_step_tc_slab(_ptr(x), _ptr(hp), _ptr(cp), _ptr(self.wsplit), _ptr(self.bias), self.forget_bias,
                                            B, Xs, Y, Z, self.C, self.F, lo, hi, _lib.FLAG_RELU_IN if relu_in else 0,
-                                           _ptr(h), _ptr(c), _ptr(self._ws), self._ws.numel() * 4, _stream())
+                                           _ptr(h), _ptr(c), _ptr(self._ws) if need else None, self._ws.numel() * 4 if need else 0, _stream())
         check(rc, "mvf_convlstm_step_tc_slab")
         return h, c
 
@@ -286,12 +287,12 @@ class IdentTensorCore:
 
     def __call__(self, x, bias, scale, shift):
         B, V, X, Y, Z, Cc = x.shape
-        need = lib.mvf_ident_tc_workspace_bytes(B, V, X, Y, Z, Cc)
-        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device:
+        need = lib.mvf_ident_tc_workspace_bytes(B, V, X, Y, Z, Cc, self.Cout)
+        if need and (self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device):
             self._ws = torch.empty(need // 4, dtype=torch.float32, device=x.device)
         out = torch.empty((B, X, Y, Z, self.Cout), dtype=torch.float32, device=x.device)
         rc = lib.mvf_ident_fuse_tc(_ptr(x), _ptr(self.wsplit), _ptr(bias), _ptr(scale), _ptr(shift), B, V, X, Y, Z, Cc,
-                                   self.Cout, _ptr(out), _ptr(self._ws), self._ws.numel() * 4, _stream())
+                                   self.Cout, _ptr(out), _ptr(self._ws) if need else None, self._ws.numel() * 4 if need else 0, _stream())
         check(rc, "mvf_ident_fuse_tc")
         return out
 
@@ -347,8 +348,9 @@ class Conv3dTensorCore:
             x2 = _cuda(x2, "x2")
             if tuple(x2.shape) != (B, X, Y, Z, self.C2):
                 raise ValueError("x2 must be %s" % ((B, X, Y, Z, self.C2),))
-        need = lib.mvf_conv3d_tc_workspace_bytes(B, V, X, Y, Z, Cc, self.C2)
-        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device:
+        # 0 when the library fuses the hi/lo split into the GEMM (large 1x1x1 convolutions)
+        need = lib.mvf_conv3d_tc_workspace_bytes(self.kind, self.ksize, B, V, X, Y, Z, Cc, self.C2, self.Cout)
+        if need and (self._ws is None or self._ws.numel() * 4 < need or self._ws.device != x.device):
             self._ws = torch.empty(need // 4, dtype=torch.float32, device=x.device)
         OX, OY, OZ = self.out_dims(X, Y, Z)
         out = torch.empty((B, OX, OY, OZ, self.Cout), dtype=torch.float32, device=x.device)
@@ -358,7 +360,7 @@ class Conv3dTensorCore:
         flags = (_lib.FLAG_RELU_IN if relu_in else 0) | (_lib.FLAG_RELU_OUT if relu_out else 0)
         rc = lib.mvf_conv3d_tc(_ptr(x), _ptr(x2), _ptr(self.wsplit), _ptr(self.bias), _ptr(self.scale), _ptr(self.shift),
                                _ptr(ps), _ptr(psh), self.kind, self.ksize, B, V, X, Y, Z, Cc, self.C2, self.Cout, flags,
-                               _ptr(out), _ptr(self._ws), self._ws.numel() * 4, _stream())
+                               _ptr(out), _ptr(self._ws) if need else None, self._ws.numel() * 4 if need else 0, _stream())
         check(rc, "mvf_conv3d_tc")
         return out
 
