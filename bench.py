@@ -312,7 +312,7 @@ def run_b200(args):
                     "steps": Ke, "api": "mvf_unproject_fuse_project_host (pinned host buffers, H2D + K1 + K3 + D2H + sync)",
                     "checksum": checksum},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "unproject_fuse_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": "unproject_slot_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": k1_traffic_bytes(B), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
                          "share_of_step": k1_ms / (k1_ms + k3_ms)},
@@ -324,7 +324,7 @@ def run_b200(args):
         if world == 1 and not args.no_convlstm:
             line["k2_convlstm"] = convlstm_line(dev)
         if world == 1 and not args.no_cpu_baseline:
-            n_cpu = 12
+            n_cpu = 24
             v, s_per, threads = cpu_reference_run(1, 16, n_cpu, 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d passes over 1 scene of workload T restricted to an x-slab of 16/64 planes (524288 "
