@@ -613,11 +613,8 @@ extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, co
               make_act_map(&tm_hh, hh, B, Xin, Y, Z, F, a.BX, a.BY, a.BZ) && make_act_map(&tm_hl, hl, B, Xin, Y, Z, F, a.BX, a.BY, a.BZ) &&
               make_w_map(&tm_wh, whi, K, 4 * F) && make_w_map(&tm_wl, wlo, K, 4 * F);
     if (!ok) return MVF_ECUDA;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(convlstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
-        attr_set = true;
-    }
+    // per-device attribute: set on every call (a process may drive several GPUs)
+    if (cudaFuncSetAttribute(convlstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
     const long long mtiles = (long long)B * a.tiles_x * a.tiles_y * a.tiles_z;
     if (mtiles > 2147483647ll || F / TC_FPT > 65535) return MVF_EUNSUPPORTED;
     dim3 grid((unsigned)mtiles, F / TC_FPT);
@@ -745,11 +742,8 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
                         make_act_map(&tm_hl, hl, B * nb_mul, MX, MY, MZ, C2, a.BX, a.BY, a.BZ);
     if (!ok) return MVF_ECUDA;
     if (!in2) { tm_hh = tm_xh; tm_hl = tm_xl; }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(convlstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
-        attr_set = true;
-    }
+    // per-device attribute: set on every call (a process may drive several GPUs)
+    if (cudaFuncSetAttribute(convlstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
     const long long mtiles = (long long)B * a.tiles_x * a.tiles_y * a.tiles_z;
     const int ntiles = (Cout + TC_N - 1) / TC_N;
     if (mtiles > 2147483647ll || ntiles > 65535) return MVF_EUNSUPPORTED;
