@@ -11,12 +11,12 @@ from ._lib import LIB_PATH, launch_count, version
 from .layers import (unproj_feat, unproj_feat_notebook, grid_reas, convlstm, convlstm_step, ConvLSTMTensorCore, Conv3dTensorCore, unet_fuse,
                      proj_grid, depth_sampling, depth_sampling_conv3d, proj_grid_depth_sampling, PyramidROIAlign, refine_detections_graph,
                      DetectionLayer, ProposalLayer, non_max_suppression, unproject_fuse,
-                     unproject_fuse_project, fusion_neck, view_reduce, channel_mean, HostPipeline, set_weights, weights, reused_lay)
+                     unproject_fuse_project, fusion_neck, prepare_params, view_reduce, channel_mean, HostPipeline, set_weights, weights, reused_lay)
 
 __all__ = [
     "FusionConfig", "LIB_PATH", "launch_count", "version",
     "unproj_feat", "unproj_feat_notebook", "grid_reas", "convlstm", "convlstm_step", "ConvLSTMTensorCore", "Conv3dTensorCore",
     "unet_fuse", "proj_grid", "depth_sampling", "depth_sampling_conv3d", "proj_grid_depth_sampling", "PyramidROIAlign", "refine_detections_graph",
     "DetectionLayer", "ProposalLayer", "non_max_suppression", "unproject_fuse",
-    "unproject_fuse_project", "fusion_neck", "view_reduce", "channel_mean", "HostPipeline", "set_weights", "weights", "reused_lay",
+    "unproject_fuse_project", "fusion_neck", "prepare_params", "view_reduce", "channel_mean", "HostPipeline", "set_weights", "weights", "reused_lay",
 ]

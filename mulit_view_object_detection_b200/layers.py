@@ -63,11 +63,49 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class PreparedBN:
+    """A frozen BatchNorm already folded to device-side (scale, shift) -- see :func:`prepare_params`."""
+
+    def __init__(self, scale, shift):
+        self.scale, self.shift = scale, shift
+
+
+class PreparedDepth:
+    """depth_sampling learnables already on the device / folded to host scalars -- see :func:`prepare_params`."""
+
+    def __init__(self, w, bias, inv, shift):
+        self.w, self.bias, self.inv, self.shift = w, bias, inv, shift
+
+
+def prepare_params(params, device="cuda"):
+    """Convert a parameter dictionary (NumPy arrays, BN 4-tuples: what ``weights_io.fusion_params_from_keras`` returns) ONCE
+    into device tensors and folded BatchNorm affines, so that the per-call host work of the layers is pointer passing only
+    (and a :func:`fusion_neck` call can be captured in a CUDA graph).  The structure of the dictionary is preserved."""
+    device = torch.device(device)
+
+    def conv(v, key):
+        if isinstance(v, dict):
+            if "weight" in v and np.ndim(v["weight"]) == 1 and "dw1" not in v and key.startswith("grid_reas_depth"):
+                w, bias, inv, shift = _depth_params(key, v, int(np.size(v["weight"])), device)
+                return PreparedDepth(w, bias, inv, shift)
+            return {k: conv(x, k) for k, x in v.items()}
+        if key == "bn" and not isinstance(v, PreparedBN):
+            n = int(np.size(v[0])) if not isinstance(v[0], torch.Tensor) else v[0].numel()
+            return PreparedBN(*_bn_affine(v, n, device))
+        if isinstance(v, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(device)
+        return v
+
+    return {k: conv(v, k) for k, v in params.items()}
+
+
 def _bn_affine(bn, C_, device):
     """(scale, shift) of a frozen BatchNorm as tf.nn.batch_normalization evaluates it:
     inv = rsqrt(var + eps) * gamma ; shift = beta - mean * inv."""
     if bn is None:
         return None, None
+    if isinstance(bn, PreparedBN):
+        return bn.scale, bn.shift
     gamma, beta, mean, var = (torch.as_tensor(a, dtype=torch.float32, device=device).reshape(-1) for a in bn)
     inv = torch.rsqrt(var + BN_EPS) * gamma
     shift = beta - mean * inv
@@ -543,6 +581,8 @@ def _depth_params(name, params, S, device):
     p = params if params is not None else weights.get(name)
     if p is None:
         raise ValueError("no weights registered for depth_sampling %r (set_weights(name, weight=[S], bias=..., bn=...))" % name)
+    if isinstance(p, PreparedDepth):
+        return p.w, p.bias, p.inv, p.shift
     w = torch.as_tensor(p["weight"], dtype=torch.float32, device=device).reshape(-1).contiguous()
     if w.numel() != S:
         raise ValueError("depth conv weight must have S=%d entries" % S)

@@ -3,6 +3,7 @@ Bit-exact for voxel->pixel indices, validity masks and ray voxel indices; 1e-5 r
 features (tolerances in tests/helpers.py)."""
 import numpy as np
 import pytest
+import torch
 
 import oracle
 from helpers import small_cfg, scene, to_dev, close, random_bn, RTOL, ATOL
@@ -247,6 +248,8 @@ def test_fusion_neck_matches_oracle(mode, vanilla):
     dR, dK = to_dev(Rcam, Kmat)
     outs = m.fusion_neck(d, dR, dK, cfg, params=dparams)
     refs = oracle.fusion_neck(fmaps, Rcam, Kmat, cfg, params)
+    prepared = m.fusion_neck(d, dR, dK, cfg, params=m.prepare_params(params))       # same bits through prepared parameters
+    assert all(torch.equal(a, b) for a, b in zip(outs, prepared))
     assert len(outs) == 5
     for lvl, o, r in zip(levels, outs, refs):
         assert tuple(o.shape) == r.shape, lvl

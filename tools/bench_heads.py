@@ -92,6 +92,33 @@ ms = timed(lambda: m.unproject_fuse_project(df, dR, dK, cfg, proj_size=40, mode=
 alg = 4 * C * (4 * 40 * 40 + 48 ** 3 + 2 * 20 * 40 * 40)
 out["c2_fusion_max_48cubed_P4"] = {"ms": ms, "voxel_samples_per_s": 4 * 48 ** 3 / ms * 1e3, "algorithmic_bytes": alg,
                                    "frac_of_hbm_peak": alg / ms / 1e6 / HBM}
+# ---- c2 fusion at every pyramid level: P2..P5 maps 160/80/40/20 squared, projected at the same sizes (model_multi.py:2393-2397)
+for lvl, fs in ((2, 160), (3, 80), (4, 40), (5, 20)):
+    f_l, R_l, K_l = syn.make_scene(cfg, 1, 4, fs, fs, C, seed=2001)
+    dl = [torch.from_numpy(a).to(dev) for a in (f_l, R_l, K_l)]
+    grid_l = torch.empty((1, 48, 48, 48, C), device=dev)
+    rays_l = torch.empty((1, 20, fs, fs, C), device=dev)
+    ms1 = timed(lambda: m.unproject_fuse(dl[0], dl[1], dl[2], cfg, mode="max", out=grid_l), n=10)
+    ms3 = timed(lambda: m.proj_grid([grid_l, dl[1], dl[2]], cfg, fs, out=rays_l), n=10)
+    a1, a3 = 4 * C * (4 * fs * fs + 48 ** 3), 4 * C * 2 * 20 * fs * fs
+    out["c2_fusion_max_48cubed_P%d" % lvl] = {"k1_ms": ms1, "k3_ms": ms3, "k1_frac_of_hbm_peak": a1 / ms1 / 1e6 / HBM,
+                                              "k3_frac_of_hbm_peak": a3 / ms3 / 1e6 / HBM,
+                                              "voxel_samples_per_s": 4 * 48 ** 3 / (ms1 + ms3) * 1e3}
+    del dl, grid_l, rays_l
+# ---- the whole 'add' neck (model_multi.py:2382-2410) at c2 shapes, all five levels computed (VANILLA=True)
+ncfg = m.FusionConfig(nvox=48, nvox_z=48, samples=20, NUM_VIEWS=4, GRID_REAS="add", IMAGES_PER_GPU=1, VANILLA=True,
+                      IMAGE_SHAPE=np.array([img, img, 3]), TOP_DOWN_PYRAMID_SIZE=C)
+fm, Rn, Kn = [], None, None
+for fs in (160, 80, 40, 20, 10):
+    f_l, Rn, Kn = syn.make_scene(ncfg, 1, 4, fs, fs, C, seed=2001)
+    fm.append(torch.from_numpy(f_l).to(dev))
+Rn, Kn = torch.from_numpy(Rn).to(dev), torch.from_numpy(Kn).to(dev)
+nparams = {"grid_reas_depth_PG%d" % l: {"weight": np.full(20, 0.05, np.float32), "bias": 0.0} for l in (2, 3, 4, 5, 6)}
+nparams.update({"grid_reas_P%d" % l: {"bn": (np.ones(C, np.float32), np.zeros(C, np.float32), np.zeros(C, np.float32), np.ones(C, np.float32))}
+                for l in (2, 3, 4, 5, 6)})
+nparams = m.prepare_params(nparams, dev)
+out["fusion_neck_add_P2_P6_48cubed"] = {"ms": timed(lambda: m.fusion_neck(fm, Rn, Kn, ncfg, params=nparams), n=10, reps=3),
+                                        "launches": "2 per level (K1 sum+BN+ReLU, K3b projection + depth collapse)"}
 # ---- K2b grid_reas 'ident': [V*C -> C] 1x1x1 conv at 4 views, 48^3
 V = 4
 icfg = m.FusionConfig(nvox=48, nvox_z=48, samples=20, NUM_VIEWS=V, GRID_REAS="ident", IMAGES_PER_GPU=1,
