@@ -179,8 +179,9 @@ def measured_bf16_peak():
 
 def convlstm_line(dev):
     """K2: one ConvLSTM step of workload c3 (C = F = 256, 64^3 voxels, recurrent state present) on the tensor cores.
-    Roofline: tensor.  `achieved` counts the TF32 MMA work actually issued (3 MMAs per product for the fp32-parity
-    split); `useful` is the conv's own 2*M*K*N.  TF32 peak = half the measured bf16 rate (same datapath, half rate)."""
+    Roofline: tensor.  `achieved` counts the f16 MMA work actually issued (3 MMAs per product: the fp32-parity split
+    a*2^s = a1 + a2 in fp16 halves, fp32 accumulation); `useful` is the conv's own 2*M*K*N.  Peak = the measured
+    sustained bf16/f16 rate."""
     import torch
     import mulit_view_object_detection_b200 as m
     X, C = 64, 256
@@ -203,13 +204,13 @@ def convlstm_line(dev):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     flop = 2.0 * X ** 3 * 27 * 2 * C * 4 * C
-    peak_bf16, src = measured_bf16_peak()
-    peak = peak_bf16 / 2.0
-    return {"workload": "c3 step: ConvLSTM 3x3x3, C=F=256, 64^3 voxels, K=13824, N=1024, fp32-parity 3xTF32 split on tcgen05",
+    peak, src = measured_bf16_peak()
+    return {"workload": "c3 step: ConvLSTM 3x3x3, C=F=256, 64^3 voxels, K=13824, N=1024, fp32-parity 3xFP16 split on tcgen05 "
+                        "(operand split passes included)",
             "ms_per_step": ms, "useful_tflops": flop / ms / 1e9,
             "roofline": {"bound": "tensor", "achieved": 3.0 * flop / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
                          "frac": 3.0 * flop / ms / 1e9 / peak, "traffic": None,
-                         "peak_source": src + " / 2 for TF32", "kernel": "convlstm_tc_kernel (K2)"},
+                         "peak_source": src, "kernel": "convlstm_tc_kernel<false,true> (K2)"},
             "checksum": float(h2.double().sum())}
 
 
@@ -395,7 +396,7 @@ def run_cooperative(args):
         cfgd = workload_config(args, world)
         cfgd["sharding"] = args.strategy
         if args.strategy == "lstm_slab":
-            cfgd["workload"] = "c3: %d-view scene, %d^3 grid, recurrent voxel fusion (ConvLSTM 3x3x3, C=F=256, 3xTF32 on tcgen05), " \
+            cfgd["workload"] = "c3: %d-view scene, %d^3 grid, recurrent voxel fusion (ConvLSTM 3x3x3, C=F=256, 3xFP16 split on tcgen05), " \
                                "x-slabs + 1-voxel halo of h exchanged per step, then proj_grid" % (T["V"], T["nvox"])
             flop = 2.0 * T["nvox"] ** 3 * 27 * 2 * T["C"] * 4 * T["C"] * T["V"] * B
             extra = {"useful_tflops": flop * args.steps / (total_ms * 1e-3) / 1e12}

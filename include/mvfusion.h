@@ -117,7 +117,9 @@ int mvf_ident_fuse(const float* in, const float* weight, const float* bias,
  *     [B,2X,2Y,2Z,Cout] (DECONV).
  * out = act(bn(conv(pre(in)) + bias)); pre = optional per-input-channel affine pre_scale/pre_shift [V*C] (a depthwise
  *     1x1 conv, :472,:477) then ReLU when MVF_FLAG_RELU_IN; act = ReLU when MVF_FLAG_RELU_OUT; bn_* [Cout] or NULL.
- * Weights: mvf_conv3d_prepare(W) once per tensor.  W is the Keras kernel: Conv3D [k,k,k,Cin,Cout], Conv3DTranspose
+ * Precision: k=3 members whose sources all have a multiple of 64 channels run the split as fp16 halves (a*2^s = a1 + a2,
+ *     three f16 MMAs, twice the tf32 rate, ~5x closer to fp32 than the tf32 split); the others use the tf32 split.
+ * Weights: mvf_conv3d_prepare(W) once per tensor (same V, C, C2 as the call; the prepared format depends on them).  W is the Keras kernel: Conv3D [k,k,k,Cin,Cout], Conv3DTranspose
  *     [3,3,3,Cout,Cin]; Cin = V*C + C2.  chan_interleave = S > 1: the reference orders the input channels (c*S + s)
  *     while `in` supplies S sources of C channels (depth_sampling, :468-470).
  * ws: mvf_conv3d_tc_workspace_bytes(...) bytes of device scratch for the hi/lo halves of the activations -- 0 (ws may be
@@ -127,7 +129,7 @@ int mvf_ident_fuse(const float* in, const float* weight, const float* bias,
 #define MVF_CONV_S2   1
 #define MVF_DECONV_S2 2
 size_t mvf_conv3d_wsplit_bytes(int kind, int ksize, int Cin, int Cout);
-int mvf_conv3d_prepare(const float* W, int kind, int ksize, int Cin, int Cout, int chan_interleave,
+int mvf_conv3d_prepare(const float* W, int kind, int ksize, int V, int C, int C2, int Cout, int chan_interleave,
                        float* wsplit, void* stream);
 size_t mvf_conv3d_tc_workspace_bytes(int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout);
 int mvf_conv3d_tc(const float* in, const float* in2, const float* wsplit, const float* bias,

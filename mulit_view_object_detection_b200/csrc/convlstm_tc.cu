@@ -27,12 +27,14 @@
 //     allocator, warps 4-7 = epilogue (tcgen05.ld -> gates -> c/h stores).  2-stage smem ring
 //     (96 KB per stage: A_hi, A_lo, B_hi, B_lo), full/empty mbarriers, tcgen05.commit.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "mvf_common.cuh"
 
 namespace mvf {
 
-constexpr int TC_M = 128, TC_N = 256, TC_K = 32, TC_STAGES = 2, TC_THREADS = 256;
+constexpr int TC_M = 128, TC_N = 256, TC_K = 32, TC_STAGES = 2, TC_THREADS = 256;   // TC_K: tf32 elements per 128-byte K chunk
+constexpr int TC_K16 = 64;                                   // fp16 elements per 128-byte K chunk
 constexpr int TC_FPT = 64;                                   // filters per CTA tile (x 4 gates = TC_N)
 constexpr uint32_t TC_A_BYTES = TC_M * TC_K * 4;             // 16 KB
 constexpr uint32_t TC_B_BYTES = TC_N * TC_K * 4;             // 32 KB
@@ -52,6 +54,8 @@ struct TcArgs {
     int relu_out;
     // fused operand split: the TMA loads the RAW fp32 activation tile and warps 2-3 turn it into (hi, lo) in shared memory
     int fused_split, relu_x, relu_h;
+    // fp16 operand split: activations and weights were scaled by powers of two; the epilogue multiplies by inv_a * inv_w
+    const float* inv_scale_a; const float* inv_scale_w;
     const float* pre_scale; const float* pre_shift;
     const float* bn_scale; const float* bn_shift; float* out;
     int promote;                  // K-chunks per promotion of the partial accumulator into the master (0 = never)
@@ -92,6 +96,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 }
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=256 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// the same with A = B = f16 (format 0), for kind::f16
+constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC_F16), "r"(accumulate) : "memory");
+}
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
@@ -154,7 +164,7 @@ __device__ __forceinline__ int tap_count(int kind, int ksize, int cls) {
     return ksize == 3 ? 27 : 1;
 }
 
-template <bool IDENT>
+template <bool IDENT, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                    const __grid_constant__ CUtensorMap tm_hh, const __grid_constant__ CUtensorMap tm_hl,
@@ -194,7 +204,8 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
     uint32_t tmem_d;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_d) : "r"(tmem_slot) : "memory");
 
-    const int cx = a.C / TC_K, ch = a.has_h ? a.F / TC_K : 0;    // 32-channel chunks of x and of h_prev
+    constexpr int KC = F16 ? TC_K16 : TC_K;                       // channels per 128-byte K chunk
+    const int cx = a.C / KC, ch = a.has_h ? a.F / KC : 0;         // K chunks of x and of h_prev per tap
     const int cls = IDENT ? (int)blockIdx.z : 0;                  // output parity class (deconv)
     const int per_tap = IDENT ? a.V * cx + ch : cx + ch;
     const int nchunks = IDENT ? tap_count(a.kind, a.ksize, cls) * per_tap : 27 * per_tap;
@@ -212,13 +223,13 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
             const TapRef r = decode_tap(a.kind, a.ksize, cls, tap);
             q.dx = r.dx; q.dy = r.dy; q.dz = r.dz;
             q.from_h = kc >= a.V * cx;
-            if (q.from_h) { q.c0 = (kc - a.V * cx) * TC_K; q.krow = r.kidx * CF + a.V * a.C + q.c0; q.bidx = b * nsub + r.sub; }
-            else { q.v = kc / cx; q.c0 = (kc - q.v * cx) * TC_K; q.krow = r.kidx * CF + q.v * a.C + q.c0; q.bidx = (b * a.V + q.v) * nsub + r.sub; }
+            if (q.from_h) { q.c0 = (kc - a.V * cx) * KC; q.krow = r.kidx * CF + a.V * a.C + q.c0; q.bidx = b * nsub + r.sub; }
+            else { q.v = kc / cx; q.c0 = (kc - q.v * cx) * KC; q.krow = r.kidx * CF + q.v * a.C + q.c0; q.bidx = (b * a.V + q.v) * nsub + r.sub; }
         } else {
             const int tap = it / per_tap, kc = it - tap * per_tap;
             q.dx = tap / 9 - 1; q.dy = (tap / 3) % 3 - 1; q.dz = tap % 3 - 1;           // W[kx][ky][kz], SAME padding
             q.from_h = kc >= cx;
-            q.c0 = (q.from_h ? kc - cx : kc) * TC_K;
+            q.c0 = (q.from_h ? kc - cx : kc) * KC;
             q.krow = tap * CF + (q.from_h ? a.C : 0) + q.c0;                            // row of the K-major weight matrix
         }
         return q;
@@ -244,7 +255,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
             tma_load_2d(st + 2 * TC_A_BYTES, &tm_wh, full_bar(s), q.krow, ntile * TC_N);
             tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tm_wl, full_bar(s), q.krow, ntile * TC_N);
         }
-    } else if ((warp == 2 || warp == 3) && a.fused_split) {
+    } else if (!F16 && (warp == 2 || warp == 3) && a.fused_split) {
         // ===== operand converter: raw fp32 tile -> a_hi (in place) and a_lo, with the ReLU / depthwise affine in front of the conv.
         // The 128-byte swizzle only permutes 16-byte chunks inside a row, so the split is position-wise; the channel of a chunk
         // (needed for the per-channel affine) is (chunk ^ (row & 7)) * 4.
@@ -290,17 +301,23 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
                 mbar_wait(part_empty, (uint32_t)(grp - 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            mbar_wait(a.fused_split ? conv_bar(s) : full_bar(s), phase);
+            mbar_wait((!F16 && a.fused_split) ? conv_bar(s) : full_bar(s), phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t st = smem_base + s * TC_STAGE_BYTES;
             const uint64_t dah = umma_desc_sw128(st), dal = umma_desc_sw128(st + TC_A_BYTES);
             const uint64_t dbh = umma_desc_sw128(st + 2 * TC_A_BYTES), dbl = umma_desc_sw128(st + 2 * TC_A_BYTES + TC_B_BYTES);
 #pragma unroll
-            for (int k = 0; k < TC_K / 8; ++k) {                   // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzle atom
+            for (int k = 0; k < 4; ++k) {                          // UMMA_K = 32 B (8 tf32 / 16 f16): advance the start address inside the swizzle atom
                 const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                umma_tf32(tmem_d, dal + adv, dbh + adv, (in_grp | k) != 0);
-                umma_tf32(tmem_d, dah + adv, dbl + adv, 1u);
-                umma_tf32(tmem_d, dah + adv, dbh + adv, 1u);
+                if (F16) {
+                    umma_f16(tmem_d, dal + adv, dbh + adv, (in_grp | k) != 0);
+                    umma_f16(tmem_d, dah + adv, dbl + adv, 1u);
+                    umma_f16(tmem_d, dah + adv, dbh + adv, 1u);
+                } else {
+                    umma_tf32(tmem_d, dal + adv, dbh + adv, (in_grp | k) != 0);
+                    umma_tf32(tmem_d, dah + adv, dbl + adv, 1u);
+                    umma_tf32(tmem_d, dah + adv, dbh + adv, 1u);
+                }
             }
             umma_commit(empty_bar(s));                              // frees the smem stage when these MMAs have read it
             if (in_grp == gsz - 1 || it == nchunks - 1) umma_commit(part_full);   // partial accumulator complete
@@ -338,6 +355,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
         const bool ok = x < a.X && y < a.Y && z < a.Z;
         const long long vox = (((long long)b * a.X + x) * a.Y + y) * a.Z + z;
         const long long voxh = (((long long)b * (a.X + a.halo_lo + a.halo_hi) + x + a.halo_lo) * a.Y + y) * a.Z + z;   // h_out keeps the halo planes
+        const float inv = F16 ? __ldg(a.inv_scale_a) * __ldg(a.inv_scale_w) : 1.0f;         // exact powers of two
         if (IDENT) {
             // out[b, vox_out, co] = relu(bn(acc + bias))     (model_multi.py:449-455, :418-441)
             long long ovox = vox;
@@ -359,7 +377,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
                 if (ok && co0 < a.Cout) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float y = v[i] + a.bias[co0 + i];
+                        float y = (F16 ? v[i] * inv : v[i]) + a.bias[co0 + i];
                         if (a.bn_scale) y = fmaf(y, a.bn_scale[co0 + i], a.bn_shift[co0 + i]);
                         v[i] = a.relu_out ? fmaxf(y, 0.f) : y;
                     }
@@ -396,6 +414,7 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
     #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int f = f0 + i;
+                        if (F16) { gj[i] *= inv; gi[i] *= inv; gf[i] *= inv; go[i] *= inv; }
                         const float vj = gj[i] + a.bias[0 * a.F + f], vi = gi[i] + a.bias[1 * a.F + f];
                         const float vf = gf[i] + a.bias[2 * a.F + f], vo = go[i] + a.bias[3 * a.F + f];
                         const float c = cp[i] * sigmoid_acc(vf + a.forget_bias) + sigmoid_acc(vi) * tanhf(vj);   // :470-472
@@ -500,6 +519,88 @@ weight_split_kernel(const float* __restrict__ W, float* __restrict__ whi, float*
     whi[i] = h; wlo[i] = v - h;
 }
 
+// ---- fp16 operand split --------------------------------------------------------------------------------------------
+// a -> a1 + a2 with a1 = fp16(a * 2^s), a2 = fp16(a * 2^s - a1) (round to nearest): 22 mantissa bits in two halves that the
+// tensor core multiplies exactly and accumulates in fp32 -- a1*b1 + a1*b2 + a2*b1 at the f16 MMA rate (twice the tf32 rate) and,
+// with rounding instead of truncation, ~5x closer to fp32 than the tf32 split.  s = 14 - exponent(max|a|) per tensor (one
+// max-reduction pass, no host sync) keeps a1 below 2^14 and pushes a2 well into the normal fp16 range; the GEMM epilogue
+// multiplies by 2^-(s_a + s_w).
+__global__ void __launch_bounds__(256)
+amax_kernel(const float4* __restrict__ in, long long n4, int relu, unsigned* __restrict__ amax_bits) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = __ldg(in + i);
+        if (relu) v = relu4(v);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));     // non-negative floats order like their bit patterns
+}
+__device__ __forceinline__ float pow2_scale(unsigned amax_bits, float* inv) {
+    const float amax = __uint_as_float(amax_bits);
+    int sa = 0;
+    if (amax > 0.f && amax < 3.0e38f) { int e; frexpf(amax, &e); sa = min(max(14 - e, -100), 100); }
+    *inv = ldexpf(1.0f, -sa);
+    return ldexpf(1.0f, sa);
+}
+__device__ __forceinline__ void split_half4(float4 v, float scale, uint2* hi, uint2* lo) {
+    const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half a1 = __float2half_rn(x[i]);
+        h[i] = __half_as_ushort(a1);
+        l[i] = __half_as_ushort(__float2half_rn(x[i] - __half2float(a1)));
+    }
+    *hi = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+    *lo = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+}
+// activations: same indexing as act_split_kernel (optional ReLU, optional parity sub-lattice re-layout); tail[0] = amax bits, tail[1] <- 2^-s
+__global__ void __launch_bounds__(256)
+act_split_f16_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint2* __restrict__ lo, long long n4,
+                     int X, int Y, int Z, int C4, int relu, int s2d, unsigned* __restrict__ tail) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float inv;
+    const float scale = pow2_scale(tail[0], &inv);
+    if (i == 0) reinterpret_cast<float*>(tail)[1] = inv;
+    if (i >= n4) return;
+    float4 v = __ldg(in + i);
+    if (relu) v = relu4(v);
+    long long o = i;
+    if (s2d) {
+        long long t = i;
+        const int c4 = (int)(t % C4); t /= C4;
+        const int z = (int)(t % Z); t /= Z;
+        const int y = (int)(t % Y); t /= Y;
+        const int x = (int)(t % X); t /= X;
+        const int sub = ((x & 1) * 2 + (y & 1)) * 2 + (z & 1);
+        o = ((((t * 8 + sub) * (X / 2) + (x >> 1)) * (Y / 2) + (y >> 1)) * (Z / 2) + (z >> 1)) * C4 + c4;
+    }
+    uint2 h, l;
+    split_half4(v, scale, &h, &l);
+    hi[o] = h; lo[o] = l;
+}
+// weights -> K-major [N, K] fp16 halves.  mode 0: W [K, N];  1: Conv3DTranspose [taps, N, Cin];  2: ConvLSTM gate permutation
+// (row n' = (f / 64) * 256 + gate * 64 + f % 64  <-  column gate * F + f, F = N / 4)
+__global__ void __launch_bounds__(256)
+weight_split_f16_kernel(const float* __restrict__ W, __half* __restrict__ whi, __half* __restrict__ wlo, int K, int N, int mode, int Cin,
+                        unsigned* __restrict__ tail) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // output element, k fastest
+    float inv;
+    const float scale = pow2_scale(tail[0], &inv);
+    if (i == 0) reinterpret_cast<float*>(tail)[1] = inv;
+    if (i >= (long long)K * N) return;
+    const int k = (int)(i % K), n = (int)(i / K);
+    long long src;
+    if (mode == 1) { const int tap = k / Cin, ci = k - tap * Cin; src = ((long long)tap * N + n) * Cin + ci; }
+    else if (mode == 2) { const int F = N / 4, grp = n / TC_N, gate = (n % TC_N) / TC_FPT, fl = n % TC_FPT; src = (long long)k * N + gate * F + grp * TC_FPT + fl; }
+    else src = (long long)k * N + n;
+    const float v = W[src] * scale;
+    const __half a1 = __float2half_rn(v);
+    whi[i] = a1; wlo[i] = __float2half_rn(v - __half2float(a1));
+}
+
 // ---- host: TMA descriptors through the driver entry point (no link-time dependency on libcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -513,23 +614,33 @@ static EncodeTiledFn encode_tiled() {
     }();
     return fn;
 }
-static bool make_act_map(CUtensorMap* tm, const float* base, int B, int X, int Y, int Z, int C, int BX, int BY, int BZ) {
+static bool make_act_map(CUtensorMap* tm, const void* base, int B, int X, int Y, int Z, int C, int BX, int BY, int BZ, bool f16 = false) {
+    const cuuint64_t es = f16 ? 2 : 4;
     const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)Z, (cuuint64_t)Y, (cuuint64_t)X, (cuuint64_t)B};
-    const cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)Z * C * 4, (cuuint64_t)Y * Z * C * 4, (cuuint64_t)X * Y * Z * C * 4};
-    const cuuint32_t box[5] = {(cuuint32_t)TC_K, (cuuint32_t)BZ, (cuuint32_t)BY, (cuuint32_t)BX, 1u};
+    const cuuint64_t strides[4] = {(cuuint64_t)C * es, (cuuint64_t)Z * C * es, (cuuint64_t)Y * Z * C * es, (cuuint64_t)X * Y * Z * C * es};
+    const cuuint32_t box[5] = {(cuuint32_t)(f16 ? TC_K16 : TC_K), (cuuint32_t)BZ, (cuuint32_t)BY, (cuuint32_t)BX, 1u};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    return encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return encode_tiled()(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-static bool make_w_map(CUtensorMap* tm, const float* base, int K, int N) {
+static bool make_w_map(CUtensorMap* tm, const void* base, int K, int N, bool f16 = false) {
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)TC_K, (cuuint32_t)TC_N};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * (f16 ? 2 : 4)};
+    const cuuint32_t box[2] = {(cuuint32_t)(f16 ? TC_K16 : TC_K), (cuuint32_t)TC_N};
     const cuuint32_t estr[2] = {1, 1};
-    return encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return encode_tiled()(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// Operand format of the k=3 convolutions: fp16 halves (twice the MMA rate) whenever every source has a multiple of 64 channels.
+// MVF_TC_TF32=1 forces the tf32 split everywhere (A/B measurement); the fused in-kernel converter is tf32 only.
+static bool env_flag(const char* name) { const char* e = getenv(name); return e && atoi(e) != 0; }
+static bool want_f16(int C, int C2) {
+    static const bool off = env_flag("MVF_TC_TF32") || env_flag("MVF_TC_FUSED_SPLIT");
+    return !off && C % TC_K16 == 0 && C2 % TC_K16 == 0;
+}
+static unsigned amax_grid(long long n4) { const long long b = (n4 + 255) / 256; return (unsigned)(b < 148 * 8 ? (b > 0 ? b : 1) : 148 * 8); }
 
 }  // namespace mvf
 
@@ -546,7 +657,17 @@ extern "C" int mvf_convlstm_prepare(const float* W, int C, int F, float* wsplit,
     if (C % TC_K != 0 || F % TC_FPT != 0) return MVF_EUNSUPPORTED;
     const int K = 27 * (C + F);
     const long long total = (long long)K * 4 * F;
-    convlstm_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, wsplit, wsplit + total, K, F);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (want_f16(C, F)) {                               // [hi K*4F halves][lo K*4F halves][amax bits, 2^-s]
+        __half* whi = (__half*)wsplit;
+        unsigned* tail = (unsigned*)(whi + 2 * total);
+        if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
+        amax_kernel<<<amax_grid(total / 4), 256, 0, s>>>((const float4*)W, total / 4, 0, tail);
+        weight_split_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, whi, whi + total, K, 4 * F, 2, C + F, tail);
+        count_launch(2);
+        return check_launch();
+    }
+    convlstm_prepare_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, wsplit, wsplit + total, K, F);
     count_launch();
     return check_launch();
 }
@@ -554,7 +675,7 @@ extern "C" int mvf_convlstm_prepare(const float* W, int C, int F, float* wsplit,
 extern "C" size_t mvf_convlstm_tc_workspace_bytes(int B, int X, int Y, int Z, int C, int F) {
     if (B <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || F <= 0) return 0;
     const size_t vox = (size_t)B * X * Y * Z;
-    return 2 * vox * (size_t)(C + F) * sizeof(float);                 // x_hi, x_lo, h_hi, h_lo
+    return 2 * vox * (size_t)(C + F) * sizeof(float) + 256;           // x_hi, x_lo, h_hi, h_lo (+ the scale cell of the fp16 split)
 }
 
 extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, const float* c_prev, const float* wsplit,
@@ -578,12 +699,28 @@ extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, co
     if (!encode_tiled()) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
     const long long vox = (long long)B * Xin * Y * Z;
-    const float *xh = x, *xl = x, *hh = h_prev ? h_prev : x, *hl = hh;
-    if (split_pass) {
+    const bool f16 = split_pass && want_f16(C, F);
+    const void *xh = x, *xl = x, *hh = h_prev ? h_prev : x, *hl = hh;
+    const float* inv_a = nullptr;
+    const int relu_in = (flags & MVF_FLAG_RELU_IN) != 0;
+    if (f16) {
+        __half* w0 = (__half*)ws;
+        __half* w1 = w0 + vox * C; __half* w2 = w1 + vox * C; __half* w3 = w2 + vox * F;
+        unsigned* tail = (unsigned*)(((uintptr_t)(w3 + vox * F) + 15) & ~(uintptr_t)15);
+        const long long n4 = vox * C / 4, m4 = vox * F / 4;
+        if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
+        amax_kernel<<<amax_grid(n4), 256, 0, s>>>((const float4*)x, n4, relu_in, tail);
+        if (h_prev) amax_kernel<<<amax_grid(m4), 256, 0, s>>>((const float4*)h_prev, m4, 0, tail);     // x and h share the accumulator: one scale
+        act_split_f16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)x, (uint2*)w0, (uint2*)w1, n4, Xin, Y, Z, C / 4, relu_in, 0, tail);
+        if (h_prev) act_split_f16_kernel<<<(unsigned)((m4 + 255) / 256), 256, 0, s>>>((const float4*)h_prev, (uint2*)w2, (uint2*)w3, m4, Xin, Y, Z, F / 4, 0, 0, tail);
+        count_launch(h_prev ? 4 : 2);
+        xh = w0; xl = w1; hh = h_prev ? (const void*)w2 : (const void*)w0; hl = h_prev ? (const void*)w3 : (const void*)w1;
+        inv_a = (const float*)tail + 1;
+    } else if (split_pass) {
         float* w0 = (float*)ws;
         float* w1 = w0 + vox * C; float* w2 = w1 + vox * C; float* w3 = w2 + vox * F;
         const long long n4 = vox * C / 4;
-        tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)x, (float4*)w0, (float4*)w1, n4, (flags & MVF_FLAG_RELU_IN) != 0);
+        tf32_split_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)x, (float4*)w0, (float4*)w1, n4, relu_in);
         count_launch();
         if (h_prev) {
             const long long m4 = vox * F / 4;
@@ -601,24 +738,33 @@ extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, co
     a.tiles_z = (Z + a.BZ - 1) / a.BZ; a.tiles_y = (Y + a.BY - 1) / a.BY; a.tiles_x = (X + a.BX - 1) / a.BX;
     a.has_h = h_prev != nullptr; a.forget_bias = forget_bias;
     a.halo_lo = halo_lo; a.halo_hi = halo_hi;
-    a.fused_split = !split_pass; a.relu_x = (flags & MVF_FLAG_RELU_IN) != 0; a.relu_h = 0; a.pre_scale = nullptr; a.pre_shift = nullptr;
+    a.fused_split = !split_pass; a.relu_x = relu_in; a.relu_h = 0; a.pre_scale = nullptr; a.pre_shift = nullptr;
     a.V = 1; a.Cout = 0; a.kind = 0; a.ksize = 3; a.relu_out = 0; a.bn_scale = nullptr; a.bn_shift = nullptr; a.out = nullptr;
     // K-chunks (of 32) per partial accumulation chain; MVF_TC_PROMOTE overrides (0 = one long chain, for A/B measurement)
     static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
     a.promote = promote_env >= 0 ? promote_env : 8;
     const int K = 27 * (C + F);
-    const float* whi = wsplit; const float* wlo = wsplit + (long long)K * 4 * F;
+    const long long wtotal = (long long)K * 4 * F;
+    const void *whi = wsplit, *wlo = wsplit + wtotal;
+    a.inv_scale_a = inv_a; a.inv_scale_w = nullptr;
+    if (f16) { whi = wsplit; wlo = (const __half*)wsplit + wtotal; a.inv_scale_w = (const float*)((const __half*)wsplit + 2 * wtotal) + 1; }
     CUtensorMap tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl;
-    bool ok = make_act_map(&tm_xh, xh, B, Xin, Y, Z, C, a.BX, a.BY, a.BZ) && make_act_map(&tm_xl, xl, B, Xin, Y, Z, C, a.BX, a.BY, a.BZ) &&
-              make_act_map(&tm_hh, hh, B, Xin, Y, Z, F, a.BX, a.BY, a.BZ) && make_act_map(&tm_hl, hl, B, Xin, Y, Z, F, a.BX, a.BY, a.BZ) &&
-              make_w_map(&tm_wh, whi, K, 4 * F) && make_w_map(&tm_wl, wlo, K, 4 * F);
+    bool ok = make_act_map(&tm_xh, xh, B, Xin, Y, Z, C, a.BX, a.BY, a.BZ, f16) && make_act_map(&tm_xl, xl, B, Xin, Y, Z, C, a.BX, a.BY, a.BZ, f16) &&
+              make_act_map(&tm_hh, hh, B, Xin, Y, Z, h_prev ? F : C, a.BX, a.BY, a.BZ, f16) &&
+              make_act_map(&tm_hl, hl, B, Xin, Y, Z, h_prev ? F : C, a.BX, a.BY, a.BZ, f16) &&
+              make_w_map(&tm_wh, whi, K, 4 * F, f16) && make_w_map(&tm_wl, wlo, K, 4 * F, f16);
     if (!ok) return MVF_ECUDA;
-    // per-device attribute: set on every call (a process may drive several GPUs)
-    if (cudaFuncSetAttribute(convlstm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
     const long long mtiles = (long long)B * a.tiles_x * a.tiles_y * a.tiles_z;
     if (mtiles > 2147483647ll || F / TC_FPT > 65535) return MVF_EUNSUPPORTED;
     dim3 grid((unsigned)mtiles, F / TC_FPT);
-    convlstm_tc_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
+    // per-device attribute: set on every call (a process may drive several GPUs)
+    if (f16) {
+        if (cudaFuncSetAttribute(convlstm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
+        convlstm_tc_kernel<false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
+    } else {
+        if (cudaFuncSetAttribute(convlstm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
+        convlstm_tc_kernel<false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
+    }
     count_launch();
     return check_launch();
 }
@@ -636,20 +782,33 @@ static int conv_taps(int kind, int ksize) { return (kind == MVF_CONV_S1 && ksize
 
 extern "C" size_t mvf_conv3d_wsplit_bytes(int kind, int ksize, int Cin, int Cout) {
     if (Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
-    return (size_t)2 * conv_taps(kind, ksize) * Cin * Cout * sizeof(float);
+    return (size_t)2 * conv_taps(kind, ksize) * Cin * Cout * sizeof(float) + 256;
 }
 
-extern "C" int mvf_conv3d_prepare(const float* W, int kind, int ksize, int Cin, int Cout, int chan_interleave,
+static bool conv3d_f16(int ksize, int C, int C2, bool pre_affine) { return ksize == 3 && !pre_affine && want_f16(C, C2); }
+
+extern "C" int mvf_conv3d_prepare(const float* W, int kind, int ksize, int V, int C, int C2, int Cout, int chan_interleave,
                                   float* wsplit, void* stream) {
     if (!W || !wsplit) return MVF_ENULL;
-    if (Cin <= 0 || Cout <= 0 || chan_interleave < 0) return MVF_EINVAL;
+    if (V <= 0 || C <= 0 || C2 < 0 || Cout <= 0 || chan_interleave < 0) return MVF_EINVAL;
     if (kind < MVF_CONV_S1 || kind > MVF_DECONV_S2 || (ksize != 1 && ksize != 3) || (kind != MVF_CONV_S1 && ksize != 3)) return MVF_EINVAL;
-    if (Cin % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
-    if (chan_interleave > 1 && (kind == MVF_DECONV_S2 || Cin % chan_interleave != 0)) return MVF_EINVAL;
+    if (C % TC_K != 0 || C2 % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
+    const int Cin = V * C + C2;
+    if (chan_interleave > 1 && (ksize != 1 || Cin % chan_interleave != 0)) return MVF_EINVAL;
     const int K = conv_taps(kind, ksize) * Cin;
     const long long total = (long long)K * Cout;
-    weight_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, wsplit, wsplit + total, K, Cout,
-                                                                                       kind == MVF_DECONV_S2, Cin, chan_interleave);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (conv3d_f16(ksize, C, C2, false)) {       // [hi K*Cout halves][lo][amax bits, 2^-s]
+        __half* whi = (__half*)wsplit;
+        unsigned* tail = (unsigned*)(whi + 2 * total);
+        if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
+        amax_kernel<<<amax_grid(total / 4), 256, 0, s>>>((const float4*)W, total / 4, 0, tail);
+        weight_split_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, whi, whi + total, K, Cout, kind == MVF_DECONV_S2 ? 1 : 0, Cin, tail);
+        count_launch(2);
+        return check_launch();
+    }
+    weight_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, wsplit, wsplit + total, K, Cout,
+                                                                      kind == MVF_DECONV_S2, Cin, chan_interleave);
     count_launch();
     return check_launch();
 }
@@ -673,7 +832,7 @@ static bool conv3d_fused_split(int kind, int ksize, int B, int X, int Y, int Z, 
 extern "C" size_t mvf_conv3d_tc_workspace_bytes(int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout) {
     if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || C2 < 0 || Cout <= 0) return 0;
     if (conv3d_fused_split(kind, ksize, B, X, Y, Z, Cout)) return 0;
-    return (size_t)2 * B * X * Y * Z * ((size_t)V * C + C2) * sizeof(float);
+    return (size_t)2 * B * X * Y * Z * ((size_t)V * C + C2) * sizeof(float) + 256;
 }
 
 extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsplit, const float* bias,
@@ -697,8 +856,21 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     if (!encode_tiled()) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
     const long long n1 = (long long)B * V * X * Y * Z * C, n2 = (long long)B * X * Y * Z * C2;
-    const float *xh = in, *xl = in, *hh = in2, *hl = in2;
-    if (split_pass) {
+    const bool f16 = split_pass && conv3d_f16(ksize, C, C2, pre_scale != nullptr);
+    const void *xh = in, *xl = in, *hh = in2, *hl = in2;
+    const float* inv_a = nullptr;
+    if (f16) {
+        __half* w0 = (__half*)ws; __half* w1 = w0 + n1; __half* w2 = w1 + n1; __half* w3 = w2 + n2;
+        unsigned* tail = (unsigned*)(((uintptr_t)(w3 + n2) + 15) & ~(uintptr_t)15);
+        if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
+        amax_kernel<<<amax_grid(n1 / 4), 256, 0, s>>>((const float4*)in, n1 / 4, relu_in, tail);
+        if (in2) amax_kernel<<<amax_grid(n2 / 4), 256, 0, s>>>((const float4*)in2, n2 / 4, relu_in, tail);      // sources share the accumulator: one scale
+        act_split_f16_kernel<<<(unsigned)((n1 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (uint2*)w0, (uint2*)w1, n1 / 4, X, Y, Z, C / 4, relu_in, s2d, tail);
+        if (in2) act_split_f16_kernel<<<(unsigned)((n2 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in2, (uint2*)w2, (uint2*)w3, n2 / 4, X, Y, Z, C2 / 4, relu_in, s2d, tail);
+        count_launch(in2 ? 4 : 2);
+        xh = w0; xl = w1; hh = w2; hl = w3;
+        inv_a = (const float*)tail + 1;
+    } else if (split_pass) {
         float* w0 = (float*)ws; float* w1 = w0 + n1; float* w2 = w1 + n1; float* w3 = w2 + n2;
         act_split_kernel<<<(unsigned)((n1 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)w0, (float4*)w1, n1 / 4, X, Y, Z, C / 4, V,
                                                                         relu_in, s2d, (const float4*)pre_scale, (const float4*)pre_shift);
@@ -733,22 +905,30 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
     a.promote = promote_env >= 0 ? promote_env : 8;
     const int K = conv_taps(kind, ksize) * (V * C + C2);
-    const float* whi = wsplit; const float* wlo = wsplit + (long long)K * Cout;
+    const long long wtotal = (long long)K * Cout;
+    const void *whi = wsplit, *wlo = wsplit + wtotal;
+    a.inv_scale_a = inv_a; a.inv_scale_w = nullptr;
+    if (f16) { wlo = (const __half*)wsplit + wtotal; a.inv_scale_w = (const float*)((const __half*)wsplit + 2 * wtotal) + 1; }
     CUtensorMap tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl;
-    bool ok = make_act_map(&tm_xh, xh, B * V * nb_mul, MX, MY, MZ, C, a.BX, a.BY, a.BZ) &&
-              make_act_map(&tm_xl, xl, B * V * nb_mul, MX, MY, MZ, C, a.BX, a.BY, a.BZ) &&
-              make_w_map(&tm_wh, whi, K, Cout) && make_w_map(&tm_wl, wlo, K, Cout);
-    if (ok && in2) ok = make_act_map(&tm_hh, hh, B * nb_mul, MX, MY, MZ, C2, a.BX, a.BY, a.BZ) &&
-                        make_act_map(&tm_hl, hl, B * nb_mul, MX, MY, MZ, C2, a.BX, a.BY, a.BZ);
+    bool ok = make_act_map(&tm_xh, xh, B * V * nb_mul, MX, MY, MZ, C, a.BX, a.BY, a.BZ, f16) &&
+              make_act_map(&tm_xl, xl, B * V * nb_mul, MX, MY, MZ, C, a.BX, a.BY, a.BZ, f16) &&
+              make_w_map(&tm_wh, whi, K, Cout, f16) && make_w_map(&tm_wl, wlo, K, Cout, f16);
+    if (ok && in2) ok = make_act_map(&tm_hh, hh, B * nb_mul, MX, MY, MZ, C2, a.BX, a.BY, a.BZ, f16) &&
+                        make_act_map(&tm_hl, hl, B * nb_mul, MX, MY, MZ, C2, a.BX, a.BY, a.BZ, f16);
     if (!ok) return MVF_ECUDA;
     if (!in2) { tm_hh = tm_xh; tm_hl = tm_xl; }
-    // per-device attribute: set on every call (a process may drive several GPUs)
-    if (cudaFuncSetAttribute(convlstm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
     const long long mtiles = (long long)B * a.tiles_x * a.tiles_y * a.tiles_z;
     const int ntiles = (Cout + TC_N - 1) / TC_N;
     if (mtiles > 2147483647ll || ntiles > 65535) return MVF_EUNSUPPORTED;
     dim3 grid((unsigned)mtiles, ntiles, kind == MVF_DECONV_S2 ? 8 : 1);
-    convlstm_tc_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
+    // per-device attribute: set on every call (a process may drive several GPUs)
+    if (f16) {
+        if (cudaFuncSetAttribute(convlstm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
+        convlstm_tc_kernel<true, true><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
+    } else {
+        if (cudaFuncSetAttribute(convlstm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess) return MVF_ECUDA;
+        convlstm_tc_kernel<true, false><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl, a);
+    }
     count_launch();
     return check_launch();
 }
@@ -758,7 +938,7 @@ extern "C" size_t mvf_ident_wsplit_bytes(int V, int C, int Cout) { return mvf_co
 extern "C" int mvf_ident_prepare(const float* weight, int V, int C, int Cout, float* wsplit, void* stream) {
     if (V <= 0 || C <= 0) return MVF_EINVAL;
     if (C % TC_K != 0) return MVF_EUNSUPPORTED;
-    return mvf_conv3d_prepare(weight, MVF_CONV_S1, 1, V * C, Cout, 0, wsplit, stream);
+    return mvf_conv3d_prepare(weight, MVF_CONV_S1, 1, V, C, 0, Cout, 0, wsplit, stream);
 }
 extern "C" size_t mvf_ident_tc_workspace_bytes(int B, int V, int X, int Y, int Z, int C, int Cout) {
     return mvf_conv3d_tc_workspace_bytes(MVF_CONV_S1, 1, B, V, X, Y, Z, C, 0, Cout);

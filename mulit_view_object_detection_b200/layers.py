@@ -362,8 +362,8 @@ class Conv3dTensorCore:
         self.scale, self.shift = _bn_affine(bn, self.Cout, W.device)
         nbytes = lib.mvf_conv3d_wsplit_bytes(self.kind, self.ksize, Cin, self.Cout)
         self.wsplit = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=W.device)
-        check(lib.mvf_conv3d_prepare(_ptr(W), self.kind, self.ksize, Cin, self.Cout, int(chan_interleave), _ptr(self.wsplit),
-                                     _stream()), "mvf_conv3d_prepare")
+        check(lib.mvf_conv3d_prepare(_ptr(W), self.kind, self.ksize, self.V, self.C, self.C2, self.Cout, int(chan_interleave),
+                                     _ptr(self.wsplit), _stream()), "mvf_conv3d_prepare")
         self._ws = None
 
     def out_dims(self, X, Y, Z):

@@ -35,7 +35,7 @@ def _dev_params(p):
     return out
 
 
-@pytest.mark.parametrize("X,Y,Z,Cin,Cout", [(4, 4, 8, 32, 32), (6, 4, 10, 64, 48), (2, 8, 4, 32, 272)])
+@pytest.mark.parametrize("X,Y,Z,Cin,Cout", [(4, 4, 8, 32, 32), (6, 4, 10, 64, 48), (2, 8, 4, 32, 272), (4, 4, 4, 128, 256)])
 def test_conv3d_stride2_matches_oracle(X, Y, Z, Cin, Cout):
     m = _m()
     rng = np.random.default_rng(X * Cout)
@@ -48,7 +48,7 @@ def test_conv3d_stride2_matches_oracle(X, Y, Z, Cin, Cout):
     close(got.cpu().numpy(), ref, rtol=1e-5, atol=5e-6)
 
 
-@pytest.mark.parametrize("X,Y,Z,Cin,Cout", [(2, 2, 4, 32, 32), (3, 2, 5, 64, 48), (1, 4, 2, 32, 272)])
+@pytest.mark.parametrize("X,Y,Z,Cin,Cout", [(2, 2, 4, 32, 32), (3, 2, 5, 64, 48), (1, 4, 2, 32, 272), (2, 2, 2, 192, 64)])
 def test_conv3d_transpose_stride2_matches_oracle(X, Y, Z, Cin, Cout):
     m = _m()
     rng = np.random.default_rng(Z * Cout)
@@ -82,7 +82,7 @@ def test_stride2_rejects_odd_dims():
         conv(to_dev(rng.standard_normal((1, 3, 4, 4, 32)).astype(np.float32))[0])
 
 
-@pytest.mark.parametrize("B,V,X,Z,C,F", [(1, 3, 8, 8, 32, 32), (2, 2, 4, 12, 32, 16)])
+@pytest.mark.parametrize("B,V,X,Z,C,F", [(1, 3, 8, 8, 32, 32), (2, 2, 4, 12, 32, 16), (1, 2, 8, 8, 64, 64)])
 def test_grid_reas_conv3d_unet(B, V, X, Z, C, F):
     """grid_reas('conv3d') (model_multi.py:406-441): U-Net over the view-concatenated grids."""
     m = _m()

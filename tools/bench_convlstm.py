@@ -28,7 +28,7 @@ for has_h in (False, True):
     ms = e0.elapsed_time(e1) / n
     K = 27 * (C + (F if has_h else 0))
     flop = 2.0 * X ** 3 * K * 4 * F
-    print("tc   has_h=%d  %.2f ms/step  %.1f TFLOP/s useful (x3 MMA work: %.1f TF/s tf32)" % (has_h, ms, flop / ms / 1e9, 3 * flop / ms / 1e9))
+    print("tc   has_h=%d  %.2f ms/step  %.1f TFLOP/s useful (x3 MMA work: %.1f TF/s of f16 MMA)" % (has_h, ms, flop / ms / 1e9, 3 * flop / ms / 1e9))
 if run_fp32:
     hf, cf = m.convlstm_step(x, h, c, W, b)
     torch.cuda.synchronize()
