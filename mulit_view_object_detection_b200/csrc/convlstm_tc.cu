@@ -214,19 +214,22 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
     const int gsz = a.promote > 0 ? a.promote : nchunks;         // K-chunks per partial accumulation chain
     const int ngroups = (nchunks + gsz - 1) / gsz;
 
-    // K-chunk `it` -> source (x view v / h), channel offset, tap shift, weight row, batch slice of the TMA tensor
+    // K-chunk `it` -> source (x view v / h), channel offset, tap shift, weight row, batch slice of the TMA tensor.
+    // Channel-chunk-major, tap-minor: consecutive chunks read the SAME channels of boxes shifted by one voxel, so all but the
+    // first of a chunk's 27 A tiles are L2 hits (tap-major order re-read each box only after a full sweep of the channels,
+    // 40-100 MB later across the 148 CTAs in flight).
     struct Chunk { int dx, dy, dz, c0, krow, bidx, v; bool from_h; };
+    const int ntaps = IDENT ? tap_count(a.kind, a.ksize, cls) : 27;
     auto decode_chunk = [&](int it) {
         Chunk q = {0, 0, 0, 0, 0, b, 0, false};
-        if (IDENT) {                                     // tap-major; inside a tap: view 0 chunks, ..., view V-1 chunks, h chunks
-            const int tap = it / per_tap, kc = it - tap * per_tap;
+        const int kc = it / ntaps, tap = it - kc * ntaps;
+        if (IDENT) {                                     // kc: view 0 chunks, ..., view V-1 chunks, h chunks
             const TapRef r = decode_tap(a.kind, a.ksize, cls, tap);
             q.dx = r.dx; q.dy = r.dy; q.dz = r.dz;
             q.from_h = kc >= a.V * cx;
             if (q.from_h) { q.c0 = (kc - a.V * cx) * KC; q.krow = r.kidx * CF + a.V * a.C + q.c0; q.bidx = b * nsub + r.sub; }
             else { q.v = kc / cx; q.c0 = (kc - q.v * cx) * KC; q.krow = r.kidx * CF + q.v * a.C + q.c0; q.bidx = (b * a.V + q.v) * nsub + r.sub; }
         } else {
-            const int tap = it / per_tap, kc = it - tap * per_tap;
             q.dx = tap / 9 - 1; q.dy = (tap / 3) % 3 - 1; q.dz = tap % 3 - 1;           // W[kx][ky][kz], SAME padding
             q.from_h = kc >= cx;
             q.c0 = (q.from_h ? kc - cx : kc) * KC;
