@@ -178,11 +178,15 @@ int mvf_convlstm_step_tc(const float* x, const float* h_prev, const float* c_pre
  * x, h_prev and h_out carry halo_lo + X + halo_hi planes in x (halo_* in {0,1}: 1 where a neighbouring slab exists,
  * its plane filled by the caller's halo exchange; 0 at the grid border, where SAME padding applies); c_prev and
  * c_out carry X planes.  h_out is written at planes [halo_lo, halo_lo + X); its halo planes are left untouched.
- * ws: mvf_convlstm_tc_workspace_bytes(B, halo_lo + X + halo_hi, Y, Z, C, F). */
+ * ws: mvf_convlstm_tc_workspace_bytes(B, halo_lo + X + halo_hi, Y, Z, C, F).
+ * act_amax: NULL, or a DEVICE pointer to max(|x| after the optional ReLU, |h_prev|) over the WHOLE grid: the fp16 operand
+ *     split scales by a power of two derived from it, and slabs of one grid must use the same scale for the sharded
+ *     recurrence to be bit-identical to the unsharded one (dist.lstm_slab all-reduces it).  NULL: computed over this call's
+ *     tensors. */
 int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, const float* c_prev, const float* wsplit,
                               const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
                               int halo_lo, int halo_hi, int flags, float* h_out, float* c_out,
-                              void* ws, size_t ws_bytes, void* stream);
+                              void* ws, size_t ws_bytes, const float* act_amax, void* stream);
 
 /* ---- K3: proj_grid ---------------------------------------------------------------------------
  * replaces proj_grid([grid,Rcam,Kmat], config, proj_size)  model_multi.py:231-322 + nearest3 :357-369

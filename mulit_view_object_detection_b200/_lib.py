@@ -63,7 +63,7 @@ _SIGS = {
     "mvf_convlstm_prepare": (_i, [_p, _i, _i, _p, _p]),
     "mvf_convlstm_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "mvf_convlstm_step_tc": (_i, [_p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
-    "mvf_convlstm_step_tc_slab": (_i, [_p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "mvf_convlstm_step_tc_slab": (_i, [_p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p, _p]),
     "mvf_project_rays": (_i, [_p, _p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _p]),
     "mvf_project_depth_collapse": (_i, [_p, _p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i,
                                         _p, _f, _f, _f, _p, _p]),

@@ -684,7 +684,7 @@ extern "C" size_t mvf_convlstm_tc_workspace_bytes(int B, int X, int Y, int Z, in
 extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, const float* c_prev, const float* wsplit,
                                          const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
                                          int halo_lo, int halo_hi, int flags, float* h_out, float* c_out,
-                                         void* ws, size_t ws_bytes, void* stream) {
+                                         void* ws, size_t ws_bytes, const float* act_amax, void* stream) {
     if (!x || !wsplit || !bias || !h_out || !c_out) return MVF_ENULL;
     if (B <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || F <= 0) return MVF_EINVAL;
     if (halo_lo < 0 || halo_lo > 1 || halo_hi < 0 || halo_hi > 1) return MVF_EINVAL;
@@ -711,12 +711,17 @@ extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, co
         __half* w1 = w0 + vox * C; __half* w2 = w1 + vox * C; __half* w3 = w2 + vox * F;
         unsigned* tail = (unsigned*)(((uintptr_t)(w3 + vox * F) + 15) & ~(uintptr_t)15);
         const long long n4 = vox * C / 4, m4 = vox * F / 4;
-        if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
-        amax_kernel<<<amax_grid(n4), 256, 0, s>>>((const float4*)x, n4, relu_in, tail);
-        if (h_prev) amax_kernel<<<amax_grid(m4), 256, 0, s>>>((const float4*)h_prev, m4, 0, tail);     // x and h share the accumulator: one scale
+        if (act_amax) {                                  // the caller's max(|relu?(x)|, |h|): slabs of one grid must agree on the scale
+            if (cudaMemcpyAsync(tail, act_amax, 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return MVF_ECUDA;
+        } else {
+            if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
+            amax_kernel<<<amax_grid(n4), 256, 0, s>>>((const float4*)x, n4, relu_in, tail);
+            if (h_prev) amax_kernel<<<amax_grid(m4), 256, 0, s>>>((const float4*)h_prev, m4, 0, tail);   // x and h share the accumulator: one scale
+            count_launch(h_prev ? 2 : 1);
+        }
         act_split_f16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>((const float4*)x, (uint2*)w0, (uint2*)w1, n4, Xin, Y, Z, C / 4, relu_in, 0, tail);
         if (h_prev) act_split_f16_kernel<<<(unsigned)((m4 + 255) / 256), 256, 0, s>>>((const float4*)h_prev, (uint2*)w2, (uint2*)w3, m4, Xin, Y, Z, F / 4, 0, 0, tail);
-        count_launch(h_prev ? 4 : 2);
+        count_launch(h_prev ? 2 : 1);
         xh = w0; xl = w1; hh = h_prev ? (const void*)w2 : (const void*)w0; hl = h_prev ? (const void*)w3 : (const void*)w1;
         inv_a = (const float*)tail + 1;
     } else if (split_pass) {
@@ -776,7 +781,7 @@ extern "C" int mvf_convlstm_step_tc(const float* x, const float* h_prev, const f
                                     const float* bias, float forget_bias, int B, int X, int Y, int Z, int C, int F,
                                     int flags, float* h_out, float* c_out, void* ws, size_t ws_bytes, void* stream) {
     return mvf_convlstm_step_tc_slab(x, h_prev, c_prev, wsplit, bias, forget_bias, B, X, Y, Z, C, F, 0, 0, flags, h_out, c_out,
-                                     ws, ws_bytes, stream);
+                                     ws, ws_bytes, nullptr, stream);
 }
 
 // ---- the plain conv3d family on the tensor cores: grid_reas 'ident' / 'conv3d' (model_multi.py:406-455), depth_sampling

@@ -264,7 +264,13 @@ def lstm_slab(feats, Rcam, Kmat, config, params, proj_size=None, group=None, ops
         # view t unprojected for the slab and its halo planes; a 1-view 'sum' is the per-view grid itself
         x_t = ops.unproject_fuse(feats[:, t:t + 1].contiguous(), Rcam[:, t:t + 1].contiguous(), Kmat, config, "sum",
                                  Rmain=Rmain, x_slab=(xb - lo, xc + lo + hi))
-        h, c = cell.step_slab(x_t, h, c, (lo, hi), relu_in=True)
+        # the fp16 operand split scales by a power of two taken from max|operand|: agree on it across the slabs
+        # (4-byte all-reduce) so that the sharded recurrence is bit-identical to the unsharded one
+        amax = x_t.amax().clamp_min(0).reshape(1)
+        if h is not None:
+            amax = torch.maximum(amax, h.abs().amax().reshape(1))
+        _all_reduce(amax, dist.ReduceOp.MAX, group)
+        h, c = cell.step_slab(x_t, h, c, (lo, hi), relu_in=True, act_amax=amax)
         if t + 1 < V:
             exchange_halo(h, lo, hi, group)
     slab = ops.affine_relu(h[:, lo:lo + xc], params.get("bn"))

@@ -276,10 +276,12 @@ class ConvLSTMTensorCore:
         return h, c
 
 
-    def step_slab(self, x, h_prev, c_prev, halo, relu_in=False, h_out=None):
+    def step_slab(self, x, h_prev, c_prev, halo, relu_in=False, h_out=None, act_amax=None):
         """Slab form (mvf_convlstm_step_tc_slab): ``x`` [B,lo+Xs+hi,Y,Z,C] and ``h_prev`` / returned ``h`` [B,lo+Xs+hi,Y,Z,F]
         carry the halo planes ``halo = (lo, hi)``; ``c_prev`` / returned ``c`` are [B,Xs,Y,Z,F].  Only the interior planes
-        of ``h`` are written; the caller fills the halo planes (dist.exchange_halo)."""
+        of ``h`` are written; the caller fills the halo planes (dist.exchange_halo).  ``act_amax``: 1-element device tensor
+        holding max(|relu?(x)|, |h_prev|) over the WHOLE grid (all slabs), so that every slab splits its operands with
+        the same power-of-two scale."""
         x = _cuda(x, "x")
         lo, hi = int(halo[0]), int(halo[1])
         B, Xin, Y, Z, Cc = x.shape
@@ -295,7 +297,8 @@ class ConvLSTMTensorCore:
         cp = _cuda(c_prev, "c_prev") if c_prev is not None else None
         rc = lib.mvf_convlstm_step_tc_slab(_ptr(x), _ptr(hp), _ptr(cp), _ptr(self.wsplit), _ptr(self.bias), self.forget_bias,
                                            B, Xs, Y, Z, self.C, self.F, lo, hi, _lib.FLAG_RELU_IN if relu_in else 0,
-                                           _ptr(h), _ptr(c), _ptr(self._ws) if need else None, self._ws.numel() * 4 if need else 0, _stream())
+                                           _ptr(h), _ptr(c), _ptr(self._ws) if need else None, self._ws.numel() * 4 if need else 0,
+                                           _ptr(act_amax), _stream())
         check(rc, "mvf_convlstm_step_tc_slab")
         return h, c
 

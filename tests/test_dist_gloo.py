@@ -55,7 +55,7 @@ class OracleCell:
     def __init__(self, W, b):
         self.W, self.b = W, b
 
-    def step_slab(self, x, h_prev, c_prev, halo, relu_in=False):
+    def step_slab(self, x, h_prev, c_prev, halo, relu_in=False, act_amax=None):
         lo, hi = halo
         xn = x.numpy()
         B, Xin = xn.shape[:2]

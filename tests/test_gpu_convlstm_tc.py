@@ -109,17 +109,20 @@ def test_tc_slab_steps_with_halo_match_full_grid():
     dW, db = to_dev(W, b)
     dx = to_dev(*xs)
     cell = m.ConvLSTMTensorCore(dW, db, 1.0)
-    h = c = None
-    for t in range(3):
-        h, c = cell.step(dx[t], h, c, relu_in=True)
     # slabs: rank 0 owns x in [0,4) (halo on the high side), rank 1 owns [4,6) (halo on the low side)
     spans = [(0, 4, 0, 1), (4, 2, 1, 0)]
     hs, cs = [None, None], [None, None]
+    h = c = None
     for t in range(3):
+        # the operand scale of the fp16 split comes from max|operand| over the WHOLE grid (dist.lstm_slab all-reduces it)
+        amax = dx[t].amax().clamp_min(0).reshape(1)
+        if h is not None:
+            amax = torch.maximum(amax, h.abs().amax().reshape(1))
+        h, c = cell.step(dx[t], h, c, relu_in=True)                      # the unsharded recurrence
         new = []
         for r, (xb, xc, lo, hi) in enumerate(spans):
             x_pad = dx[t][:, xb - lo:xb + xc + hi].contiguous()
-            new.append(cell.step_slab(x_pad, hs[r], cs[r], (lo, hi), relu_in=True))
+            new.append(cell.step_slab(x_pad, hs[r], cs[r], (lo, hi), relu_in=True, act_amax=amax))
         (h0, c0), (h1, c1) = new
         h0[:, 4].copy_(h1[:, 1])          # rank 1's first interior plane -> rank 0's high halo
         h1[:, 0].copy_(h0[:, 3])          # rank 0's last interior plane  -> rank 1's low halo
