@@ -334,16 +334,16 @@ convlstm_tc_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_const
             mbar_wait(part_full, (uint32_t)grp & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int c16 = 0; c16 < TC_N; c16 += 16) {
-                float pv[16], mv[16];
-                tmem_ld16(tpart + c16, pv);
-                if (grp > 0) tmem_ld16(tmast + c16, mv);
+            for (int c32 = 0; c32 < TC_N; c32 += 32) {              // 32 columns per round trip: 4 loads in flight, one wait
+                float pa[16], pb[16], ma[16], mb[16];
+                tmem_ld16(tpart + c32, pa); tmem_ld16(tpart + c32 + 16, pb);
+                if (grp > 0) { tmem_ld16(tmast + c32, ma); tmem_ld16(tmast + c32 + 16, mb); }
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (grp > 0) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) pv[i] += mv[i];
+                    for (int i = 0; i < 16; ++i) { pa[i] += ma[i]; pb[i] += mb[i]; }
                 }
-                tmem_st16(tmast + c16, pv);
+                tmem_st16(tmast + c32, pa); tmem_st16(tmast + c32 + 16, pb);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
