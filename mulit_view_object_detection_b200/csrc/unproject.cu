@@ -47,7 +47,7 @@ struct UnprojParams {
 //   phase B (lanes = float4 channel slots): walk the run.
 constexpr int RUN_WARPS = 8, RUN_TX = 4, RUN_TY = 2;
 
-template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC>
+template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC, bool AUX>
 __global__ void __launch_bounds__(RUN_WARPS * 32, (CPL * L <= 16) ? 2 : 1)
 unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zsplit) {
     constexpr int VPP = 32 / L;                       // views handled per phase A
@@ -185,7 +185,7 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
                         w4 = make_float4(mul_rn(wy0, wx0), mul_rn(wy0, wx1), mul_rn(wy1, wx0), mul_rn(wy1, wx1));
                     }
                 }
-                if (chunk == 0 && (p.out_idx || p.out_valid)) {
+                if (AUX && chunk == 0) {                  // index / validity side outputs (parity tests): compiled out of the production kernel
                     const size_t vox = (((size_t)b * V + v) * p.Xs + ixs) * p.Y * p.Z + (size_t)iy * p.Z + iz;
                     if (p.out_idx) { p.out_idx[vox * 2 + 0] = y0; p.out_idx[vox * 2 + 1] = x0; }
                     if (p.out_valid) p.out_valid[vox] = (uint8_t)bits;
@@ -376,13 +376,13 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
     }   // z-tile loop
 }
 
-template <int CPL, int L, bool RELU_IN, bool FULLC>
+template <int CPL, int L, bool RELU_IN, bool FULLC, bool AUX>
 static int launch_run_mode(const UnprojParams& p, dim3 grid, int nchunk, int zsplit, cudaStream_t s) {
     switch (p.mode) {
-        case MVF_FUSE_NONE: unproject_slot_kernel<CPL, L, MVF_FUSE_NONE, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
-        case MVF_FUSE_SUM:  unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
-        case MVF_FUSE_MEAN: unproject_slot_kernel<CPL, L, MVF_FUSE_MEAN, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
-        case MVF_FUSE_MAX:  unproject_slot_kernel<CPL, L, MVF_FUSE_MAX, RELU_IN, FULLC><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_NONE: unproject_slot_kernel<CPL, L, MVF_FUSE_NONE, RELU_IN, FULLC, AUX><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_SUM:  unproject_slot_kernel<CPL, L, MVF_FUSE_SUM, RELU_IN, FULLC, AUX><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_MEAN: unproject_slot_kernel<CPL, L, MVF_FUSE_MEAN, RELU_IN, FULLC, AUX><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
+        case MVF_FUSE_MAX:  unproject_slot_kernel<CPL, L, MVF_FUSE_MAX, RELU_IN, FULLC, AUX><<<grid, RUN_WARPS * 32, 0, s>>>(p, nchunk, zsplit); break;
         default: return MVF_EINVAL;
     }
     count_launch();
@@ -406,8 +406,12 @@ static int launch_run(const UnprojParams& p, int B, cudaStream_t s) {
     dim3 grid((unsigned)(cols * zsplit), B * nchunk);
     const bool fullc = (C4 % (32 * CPL)) == 0;
     const bool relu_in = (p.flags & MVF_FLAG_RELU_IN) != 0;
-    if (fullc) return relu_in ? launch_run_mode<CPL, L, true, true>(p, grid, nchunk, zsplit, s) : launch_run_mode<CPL, L, false, true>(p, grid, nchunk, zsplit, s);
-    return relu_in ? launch_run_mode<CPL, L, true, false>(p, grid, nchunk, zsplit, s) : launch_run_mode<CPL, L, false, false>(p, grid, nchunk, zsplit, s);
+    if (p.out_idx || p.out_valid) {       // side outputs requested: the (rare) instrumented build
+        if (fullc) return relu_in ? launch_run_mode<CPL, L, true, true, true>(p, grid, nchunk, zsplit, s) : launch_run_mode<CPL, L, false, true, true>(p, grid, nchunk, zsplit, s);
+        return relu_in ? launch_run_mode<CPL, L, true, false, true>(p, grid, nchunk, zsplit, s) : launch_run_mode<CPL, L, false, false, true>(p, grid, nchunk, zsplit, s);
+    }
+    if (fullc) return relu_in ? launch_run_mode<CPL, L, true, true, false>(p, grid, nchunk, zsplit, s) : launch_run_mode<CPL, L, false, true, false>(p, grid, nchunk, zsplit, s);
+    return relu_in ? launch_run_mode<CPL, L, true, false, false>(p, grid, nchunk, zsplit, s) : launch_run_mode<CPL, L, false, false, false>(p, grid, nchunk, zsplit, s);
 }
 
 // Fill the voxel-centre arrays the way the reference's tf.range calls do.
