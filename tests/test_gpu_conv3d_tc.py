@@ -116,3 +116,26 @@ def test_depth_sampling_conv3d_branch():
     ref = oracle.depth_sampling_conv3d(x, params)
     assert tuple(out.shape) == (B, P, P, F)
     close(out.cpu().numpy(), ref, rtol=1e-5, atol=5e-6)
+
+
+def test_fp16_split_keeps_fp32_accuracy_over_a_wide_dynamic_range():
+    """The fp16 operand split scales each tensor by a power of two taken from its max; elements down to ~4e-7 of the max
+    are still represented to 1e-5 relative (a2 goes subnormal with 2^-24 spacing in the scaled domain).  Inputs spanning
+    six decades: the output must stay within 1e-5 of its own scale."""
+    m = _m()
+    rng = np.random.default_rng(12)
+    Cin, Cout = 64, 64                                   # multiples of 64: the f16-rate path
+    p = _layer(rng, (3, 3, 3, Cin, Cout), 27 * Cin, Cout)
+    mag = 10.0 ** rng.uniform(-3, 3, (1, 4, 4, 8, Cin))
+    x = (mag * rng.choice([-1.0, 1.0], mag.shape)).astype(np.float32)
+    conv = m.Conv3dTensorCore(*to_dev(p["W"], p["b"]), "conv")
+    got = conv(to_dev(x)[0], relu_out=False).cpu().numpy()
+    ref = (oracle.fusion.conv3d_same(x, p["W"]) + p["b"]).astype(np.float32)
+    scale = float(np.abs(ref).max())
+    assert np.abs(got - ref).max() <= 1e-5 * scale
+    # and a tensor of small values only (max 1e-3) is as accurate as one of O(1) values: the scale follows the data
+    xs = (x / np.abs(x).max() * 1e-3).astype(np.float32)
+    conv0 = m.Conv3dTensorCore(to_dev(p["W"])[0], to_dev(np.zeros(Cout, np.float32))[0], "conv")       # no bias: outputs ~1e-4
+    got_s = conv0(to_dev(xs)[0], relu_out=False).cpu().numpy()
+    ref_s = oracle.fusion.conv3d_same(xs, p["W"]).astype(np.float32)
+    assert np.abs(got_s - ref_s).max() <= 1e-5 * float(np.abs(ref_s).max())
