@@ -174,49 +174,86 @@ nms_mask_kernel(const float4* s_box, const int32_t* s_cls, int n, int nwords, fl
     }
 }
 
-// greedy selection over the bit matrix; one CTA (256 threads, thread t owns removed-word t) per problem
+// greedy selection over the bit matrix; one CTA (256 threads, thread t owns removed-word t) per problem.
+// The sweep is a latency chain (one dependent round per 32 candidates), so nothing on it may wait for global memory or for a
+// single thread's shared-memory round trips:
+//   * the mask rows of the candidates two blocks ahead are prefetched into a 3-deep shared-memory ring by warps 1-7
+//     (coalesced, 8 loads in flight per thread) while warp 0 resolves the current block;
+//   * warp 0 resolves a block with every lane holding one candidate (index, class, diagonal word) in registers and the
+//     32-step dependency chain running on warp shuffles (all lanes compute the same `cur` / `kept` / `total`);
+//   * per-class counters (tf NMS stops a class at max_output_size) live in shared memory and are only touched when class
+//     ids were given.
+constexpr int SCAN_RING = 3;
 __global__ void __launch_bounds__(256)
 nms_scan_kernel(const unsigned* mask, const int32_t* s_idx, const int32_t* s_cls, int n, int nwords,
-                int max_per_class, int max_total, int by_position, int32_t* keep, int32_t* keep_count) {
-    __shared__ unsigned sh_diag[32];
-    __shared__ int sh_idx[32], sh_cls[32];
+                int max_per_class, int max_total, int by_position, int single_class, int32_t* keep, int32_t* keep_count) {
+    extern __shared__ unsigned sh_rows[];                        // [SCAN_RING][32][nwords]
     __shared__ unsigned sh_cur, sh_kept;
     __shared__ int sh_total, sh_done;
     __shared__ int sh_cnt[MVF_MAX_CLASSES];
-    const int pb = blockIdx.x, tid = threadIdx.x;
+    const int pb = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const unsigned* mp = mask + (size_t)pb * n * nwords;
     const int32_t* ip = s_idx + (size_t)pb * n;
     const int32_t* cp = s_cls + (size_t)pb * n;
     int32_t* kp = keep + (size_t)pb * max_total;
     for (int i = tid; i < MVF_MAX_CLASSES; i += blockDim.x) sh_cnt[i] = 0;
     if (tid == 0) { sh_total = 0; sh_done = 0; }
-    unsigned remv = 0;
-    __syncthreads();
-    for (int wi = 0; wi < nwords; ++wi) {
-        if (tid < 32) {
-            const int row = wi * 32 + tid;
-            sh_idx[tid] = row < n ? ip[row] : -1;
-            sh_cls[tid] = row < n ? cp[row] : -1;
-            sh_diag[tid] = row < n ? mp[(size_t)row * nwords + wi] : 0u;
+    // rows blk*32 .. blk*32+31, words >= blk (upper triangle): warp `wfirst + k*wstride` copies row k..., lanes stride over the
+    // words of a row (coalesced), up to 8 loads in flight per lane before the stores; no integer divisions on this path
+    auto load_block = [&](int blk, int wfirst, int wstride) {
+        unsigned* dst = sh_rows + (size_t)(blk % SCAN_RING) * 32 * nwords;
+        for (int r = wfirst; r < 32; r += wstride) {
+            const int row = blk * 32 + r;
+            const unsigned* src = mp + (size_t)row * nwords;
+            for (int w0 = blk + lane; w0 < nwords; w0 += 8 * 32) {
+                unsigned v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int w = w0 + 32 * u; v[u] = (row < n && w < nwords) ? __ldg(src + w) : 0u; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int w = w0 + 32 * u; if (w < nwords) dst[r * nwords + w] = v[u]; }
+            }
         }
+    };
+    load_block(0, tid >> 5, 8);
+    if (nwords > 1) load_block(1, tid >> 5, 8);
+    int nidx = -1, ncls = -1;                                     // warp 0: candidate `lane` of the next block
+    if (tid < 32) { nidx = tid < n ? ip[tid] : -1; ncls = tid < n ? cp[tid] : -1; }
+    unsigned remv = 0;
+    int total = 0;                                                // warp 0: running number of kept boxes (uniform)
+    for (int wi = 0; wi < nwords; ++wi) {
         if (tid == wi) sh_cur = remv;
-        __syncthreads();
-        if (tid == 0) {
+        __syncthreads();                                          // block wi is in shared memory, sh_cur published
+        const unsigned* rows = sh_rows + (size_t)(wi % SCAN_RING) * 32 * nwords;
+        if (tid >= 32) {
+            if (wi + 2 < nwords) load_block(wi + 2, (tid >> 5) - 1, 7);
+        } else {
+            const int idx = nidx, cls = ncls;
+            const unsigned diag = rows[lane * nwords + wi];
+            const int row = (wi + 1) * 32 + lane;                 // next block's candidates: issued now, used next iteration
+            nidx = (wi + 1 < nwords && row < n) ? ip[row] : -1;
+            ncls = (wi + 1 < nwords && row < n) ? cp[row] : -1;
             unsigned cur = sh_cur, kept = 0;
-            int total = sh_total, done = 0;
+            int done = 0;
+#pragma unroll 1
             for (int b = 0; b < 32; ++b) {
-                if (sh_idx[b] < 0) { done = 1; break; }           // past the last candidate
-                if (total >= max_total) { done = 1; break; }
+                const int bi = __shfl_sync(0xffffffffu, idx, b);
+                if (bi < 0 || total >= max_total) { done = 1; break; }    // past the last candidate / output full
                 if ((cur >> b) & 1u) continue;
-                const int c = sh_cls[b];
-                if (sh_cnt[c] >= max_per_class) continue;         // tf NMS stops a class at max_output_size
-                sh_cnt[c] += 1;
-                kp[total++] = by_position ? (wi * 32 + b) : sh_idx[b];
+                if (!single_class) {
+                    const int c = __shfl_sync(0xffffffffu, cls, b);
+                    const int cnt = sh_cnt[c];                                // broadcast read
+                    if (cnt >= max_per_class) continue;                       // tf NMS stops a class at max_output_size
+                    __syncwarp();
+                    if (lane == 0) sh_cnt[c] = cnt + 1;
+                    __syncwarp();
+                }
+                if (lane == 0) kp[total] = by_position ? (wi * 32 + b) : bi;
+                ++total;
                 kept |= 1u << b;
-                cur |= sh_diag[b];
+                cur |= __shfl_sync(0xffffffffu, diag, b);
             }
             if (total >= max_total) done = 1;
-            sh_total = total; sh_kept = kept; sh_done = done;
+            if (lane == 0) { sh_total = total; sh_kept = kept; sh_done = done; }
         }
         __syncthreads();
         if (sh_done) break;
@@ -225,14 +262,14 @@ nms_scan_kernel(const unsigned* mask, const int32_t* s_idx, const int32_t* s_cls
             while (kept) {
                 const int b = __ffs(kept) - 1;
                 kept &= kept - 1;
-                remv |= mp[(size_t)(wi * 32 + b) * nwords + tid];
+                remv |= rows[b * nwords + tid];
             }
         }
     }
     __syncthreads();
-    const int total = sh_total;
-    for (int i = total + tid; i < max_total; i += blockDim.x) kp[i] = -1;
-    if (tid == 0 && keep_count) keep_count[pb] = total;
+    const int ntotal = sh_total;
+    for (int i = ntotal + tid; i < max_total; i += blockDim.x) kp[i] = -1;
+    if (tid == 0 && keep_count) keep_count[pb] = ntotal;
 }
 
 struct NmsWs { u64* keys; int32_t* s_idx; float4* s_box; int32_t* s_cls; unsigned* mask; size_t bytes; };
@@ -255,13 +292,16 @@ static NmsWs carve_nms(void* ws, int nprob, int n, int n_pad) {
 
 // mask + scan on already gathered (score-ordered) boxes
 static int run_mask_scan(const NmsWs& w, int nprob, int n, float thr, int max_per_class, int max_total, int by_position,
-                         int32_t* keep, int32_t* keep_count, cudaStream_t s) {
+                         int single_class, int32_t* keep, int32_t* keep_count, cudaStream_t s) {
     const int nwords = (n + 31) / 32;
     dim3 gm(nwords, (n + MASK_ROWS - 1) / MASK_ROWS, nprob);
     nms_mask_kernel<<<gm, 256, 0, s>>>(w.s_box, w.s_cls, n, nwords, thr, w.mask);
     count_launch();
-    nms_scan_kernel<<<nprob, 256, 0, s>>>(w.mask, w.s_idx, w.s_cls, n, nwords, max_per_class, max_total, by_position,
-                                           keep, keep_count);
+    const size_t scan_smem = (size_t)SCAN_RING * 32 * nwords * sizeof(unsigned);   // 96 KB at the 8192-box limit
+    if (scan_smem > 32 * 1024 &&                     // static shared memory (class counters) counts against the 48 KB default
+        cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem) != cudaSuccess) return MVF_ECUDA;
+    nms_scan_kernel<<<nprob, 256, scan_smem, s>>>(w.mask, w.s_idx, w.s_cls, n, nwords, max_per_class, max_total, by_position,
+                                                   single_class, keep, keep_count);
     count_launch();
     return check_launch();
 }
@@ -366,7 +406,7 @@ extern "C" int mvf_nms(const float* boxes, const float* scores, const int32_t* c
     dim3 gg((n + 255) / 256, nprob);
     nms_gather_kernel<<<gg, 256, 0, s>>>(w.keys, (const float4*)boxes, class_ids, n, n_pad, w.s_idx, w.s_box, w.s_cls);
     count_launch();
-    return run_mask_scan(w, nprob, n, iou_threshold, max_out, max_total, 0, keep, keep_count, s);
+    return run_mask_scan(w, nprob, n, iou_threshold, max_out, max_total, 0, class_ids == nullptr && max_out >= max_total, keep, keep_count, s);
 }
 
 struct RefineWs { float4* refined; int32_t* cls; float* score; int32_t* keep; NmsWs nms; size_t bytes; };
@@ -412,7 +452,7 @@ extern "C" int mvf_refine_detections(const float* rois, const float* probs, cons
     nms_gather_kernel<<<gg, 256, 0, s>>>(w.nms.keys, w.refined, w.cls, N, n_pad, w.nms.s_idx, w.nms.s_box, w.nms.s_cls);
     count_launch();
     // per-class NMS (<= max_inst per class, :1171-1174) and top-max_inst by score (:1197-1201) in one scan
-    rc = run_mask_scan(w.nms, B, N, nms_threshold, max_inst, max_inst, 0, w.keep, out_count, s);
+    rc = run_mask_scan(w.nms, B, N, nms_threshold, max_inst, max_inst, 0, 0, w.keep, out_count, s);
     if (rc != MVF_OK) return rc;
     dim3 gw((max_inst + 127) / 128, B);
     write_detections_kernel<<<gw, 128, 0, s>>>(w.keep, w.refined, w.cls, w.score, N, max_inst, detections, out_keep);
@@ -462,7 +502,7 @@ extern "C" int mvf_proposals(const float* rpn_probs, const float* rpn_bbox, cons
     proposal_boxes_kernel<<<gb, 256, 0, s>>>(w.keys, rpn_bbox, anchors, bbox_std[0], bbox_std[1], bbox_std[2], bbox_std[3],
                                              A, a_pad, limit, w.nms.s_idx, w.nms.s_box, w.nms.s_cls);
     count_launch();
-    rc = run_mask_scan(w.nms, B, limit, nms_threshold, proposal_count, proposal_count, 1, w.keep, out_count, s);
+    rc = run_mask_scan(w.nms, B, limit, nms_threshold, proposal_count, proposal_count, 1, 1, w.keep, out_count, s);
     if (rc != MVF_OK) return rc;
     dim3 gw((proposal_count + 127) / 128, B);
     write_proposals_kernel<<<gw, 128, 0, s>>>(w.keep, w.nms.s_box, limit, proposal_count, (float4*)proposals);
