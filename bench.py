@@ -300,6 +300,27 @@ def run_b200(args):
     e2e_value = voxel_samples_step * Ke / (float(te.item()) * 1e-3)
     checksum = float(h_out.double().sum())          # the device->host result is really read
 
+    # ---- the same crossing at the boundary the reference model has (model_multi.py:2382-2404): features in, PG out --
+    # grid_reas BatchNorm + ReLU fused into K1, depth_sampling fused into the projection, so only [B,P,P,C] comes back
+    depth = {"weight": np.full(T["S"], 1.0 / T["S"], np.float32), "bias": 0.0, "bn": (1.0, 0.0, 0.0, 1.0)}
+    ones, zeros = np.ones(T["C"], np.float32), np.zeros(T["C"], np.float32)
+    neck = m.HostPipeline(cfg, B, T["V"], T["fh"], T["fw"], T["C"], T["P"], mode="sum", depth=depth,
+                          bn=(ones, zeros, zeros, ones), relu_out=True)
+    n_out = neck.empty_output()
+    for _ in range(3):
+        neck(h_in[0], h_in[1], h_in[2], n_out)
+    barrier()
+    e0.record(stream)
+    for _ in range(Ke):
+        neck(h_in[0], h_in[1], h_in[2], n_out)
+    e1.record(stream)
+    barrier()
+    tn = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+    neck_value = voxel_samples_step * Ke / (float(tn.item()) * 1e-3)
+    neck_checksum = float(n_out.double().sum())
+
     if rank == 0:
         peak, peak_src = measured_peak()
         k1_bytes, k3_bytes = algorithmic_bytes(B)
@@ -312,6 +333,10 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "steps": Ke, "api": "mvf_unproject_fuse_project_host (pinned host buffers, H2D + K1 + K3 + D2H + sync)",
                     "checksum": checksum},
+            "e2e_neck": {"value": neck_value, "unit": UNIT, "h2d_bytes_per_step": neck.h2d_bytes, "d2h_bytes_per_step": neck.d2h_bytes,
+                         "steps": Ke, "api": "mvf_fusion_neck_level_host (features in, depth-sampled PG [B,P,P,C] out: H2D + K1(+BN+ReLU) "
+                                             "+ K3b + D2H + sync) -- the host/device boundary of the reference model; extra to `e2e`",
+                         "checksum": neck_checksum},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "unproject_slot_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": k1_traffic_bytes(B), "peak_source": peak_src,

@@ -277,6 +277,18 @@ int mvf_unproject_fuse_project_host(const float* h_feats, const float* h_Rcam, c
                                     int proj_h, int proj_w, int samples,
                                     float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream);
 
+/* One pyramid level of the fusion neck (model_multi.py:2382-2404) from HOST buffers: as above, with depth_sampling (non-conv3d
+ * branch, :481-487) fused into the projection, so h_out is PG [B,ph,pw,C] and only features go in / PG comes out.
+ * d_depth_w [S] device; depth_bias / depth_bn_scale / depth_bn_shift: the folded scalars of the depth conv and its BatchNorm.
+ * Same workspace as mvf_unproject_fuse_project_host. */
+int mvf_fusion_neck_level_host(const float* h_feats, const float* h_Rcam, const float* h_Kmat,
+                               const MvfGrid* g, int B, int V, int fh, int fw, int C,
+                               int img_h, int img_w, int mode, int flags,
+                               const float* d_bn_scale, const float* d_bn_shift,
+                               int proj_h, int proj_w, int samples,
+                               const float* d_depth_w, float depth_bias, float depth_bn_scale, float depth_bn_shift,
+                               float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char* mvf_error_string(int code);
 const char* mvf_version(void);

@@ -79,6 +79,8 @@ _SIGS = {
     "mvf_pipeline_host_workspace_bytes": (_sz, [_G, _i, _i, _i, _i, _i, _i, _i, _i]),
     "mvf_unproject_fuse_project_host": (_i, [_p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p,
                                              _i, _i, _i, _p, _p, _sz, _p]),
+    "mvf_fusion_neck_level_host": (_i, [_p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p,
+                                        _i, _i, _i, _p, _f, _f, _f, _p, _p, _sz, _p]),
     "mvf_error_string": (C.c_char_p, [_i]),
     "mvf_version": (C.c_char_p, []),
     "mvf_launch_count": (C.c_ulonglong, []),

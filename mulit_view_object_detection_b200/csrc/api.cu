@@ -50,11 +50,11 @@ extern "C" size_t mvf_pipeline_host_workspace_bytes(const MvfGrid* g, int B, int
 }
 
 // Auxiliary streams/events of the host entry point, created lazily once per device (the only
-// library state besides the launch counter): copy-in + kernels run on `sc`, copy-out on `sd`, so
+// library state besides the launch counter): copy-in runs on `sh`, kernels on `sc`, copy-out on `sd`, so
 // the H2D of scene-chunk i+1, the kernels of chunk i and the D2H of chunk i-1 overlap.
 namespace {
 constexpr int kMaxChunks = 32;
-struct Aux { bool ok = false; cudaStream_t sc = nullptr, sd = nullptr; cudaEvent_t start = nullptr, done_c = nullptr, done_d = nullptr; cudaEvent_t ev[kMaxChunks] = {}; };
+struct Aux { bool ok = false; cudaStream_t sh = nullptr, sc = nullptr, sd = nullptr; cudaEvent_t start = nullptr, done_c = nullptr, done_d = nullptr; cudaEvent_t ev[kMaxChunks] = {}, ev_in[kMaxChunks + 1] = {}; };
 Aux g_aux[64];
 std::mutex g_aux_mu;
 Aux* get_aux() {
@@ -63,12 +63,14 @@ Aux* get_aux() {
     std::lock_guard<std::mutex> lock(g_aux_mu);
     Aux& a = g_aux[dev];
     if (!a.ok) {
+        if (cudaStreamCreateWithFlags(&a.sh, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithFlags(&a.sc, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         if (cudaStreamCreateWithFlags(&a.sd, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         cudaEventCreateWithFlags(&a.start, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&a.done_c, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&a.done_d, cudaEventDisableTiming);
         for (int i = 0; i < kMaxChunks; ++i) cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming);
+        for (int i = 0; i <= kMaxChunks; ++i) cudaEventCreateWithFlags(&a.ev_in[i], cudaEventDisableTiming);
         a.ok = true;
     }
     return &a;
@@ -78,12 +80,16 @@ Aux* get_aux() {
 // The reference crosses host->device once per predict() call (mrcnn/model_multi.py:3067-3068);
 // this is the same crossing for the fusion path alone: H2D inputs, K1, K3, D2H ray slices,
 // software-pipelined over chunks of scenes.
-extern "C" int mvf_unproject_fuse_project_host(const float* h_feats, const float* h_Rcam, const float* h_Kmat,
-                                               const MvfGrid* g, int B, int V, int fh, int fw, int C,
-                                               int img_h, int img_w, int mode, int flags,
-                                               const float* d_bn_scale, const float* d_bn_shift,
-                                               int proj_h, int proj_w, int samples,
-                                               float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream) {
+namespace {
+struct Collapse { const float* d_w; float bias, bn_scale, bn_shift; };       // depth_sampling fused into the projection (K3b)
+}
+
+static int host_pipeline(const float* h_feats, const float* h_Rcam, const float* h_Kmat,
+                         const MvfGrid* g, int B, int V, int fh, int fw, int C,
+                         int img_h, int img_w, int mode, int flags,
+                         const float* d_bn_scale, const float* d_bn_shift,
+                         int proj_h, int proj_w, int samples, const Collapse* col,
+                         float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream) {
     if (!h_feats || !h_Rcam || !h_Kmat || !g || !h_out || !dev_ws) return MVF_ENULL;
     if (B <= 0 || V <= 0 || fh <= 0 || fw <= 0 || C <= 0 || proj_h <= 0 || proj_w <= 0 || samples <= 0) return MVF_EINVAL;
     if (mode < MVF_FUSE_SUM || mode > MVF_FUSE_MAX) return MVF_EINVAL;
@@ -95,29 +101,39 @@ extern "C" int mvf_unproject_fuse_project_host(const float* h_feats, const float
     cudaStream_t s = (cudaStream_t)stream;
     const size_t feat_scene = (size_t)V * fh * fw * C;
     const size_t grid_scene = (size_t)g->nvox * g->nvox * g->nvox_z * C;
-    const size_t out_scene = (size_t)samples * proj_h * proj_w * C;
+    const size_t out_scene = (size_t)(col ? 1 : samples) * proj_h * proj_w * C;      // collapsed: [P,P,C] per scene
 #define MVF_TRY(x) do { if ((x) != cudaSuccess) return MVF_ECUDA; } while (0)
     // order the auxiliary streams after whatever the caller queued on `stream`
     MVF_TRY(cudaEventRecord(ax->start, s));
+    MVF_TRY(cudaStreamWaitEvent(ax->sh, ax->start, 0));
     MVF_TRY(cudaStreamWaitEvent(ax->sc, ax->start, 0));
     MVF_TRY(cudaStreamWaitEvent(ax->sd, ax->start, 0));
-    MVF_TRY(cudaMemcpyAsync(w.Rcam, h_Rcam, (size_t)B * V * 12 * sizeof(float), cudaMemcpyHostToDevice, ax->sc));
-    MVF_TRY(cudaMemcpyAsync(w.Kmat, h_Kmat, (size_t)B * 9 * sizeof(float), cudaMemcpyHostToDevice, ax->sc));
+    MVF_TRY(cudaMemcpyAsync(w.Rcam, h_Rcam, (size_t)B * V * 12 * sizeof(float), cudaMemcpyHostToDevice, ax->sh));
+    MVF_TRY(cudaMemcpyAsync(w.Kmat, h_Kmat, (size_t)B * 9 * sizeof(float), cudaMemcpyHostToDevice, ax->sh));
     // proj_grid reads the main-view poses as a contiguous [B,3,4] tensor (Rcam[:,0], model_multi.py:245)
     MVF_TRY(cudaMemcpy2DAsync(w.R0, 12 * sizeof(float), w.Rcam, (size_t)V * 12 * sizeof(float), 12 * sizeof(float), B,
-                              cudaMemcpyDeviceToDevice, ax->sc));
+                              cudaMemcpyDeviceToDevice, ax->sh));
+    MVF_TRY(cudaEventRecord(ax->ev_in[kMaxChunks], ax->sh));
+    MVF_TRY(cudaStreamWaitEvent(ax->sc, ax->ev_in[kMaxChunks], 0));
     const int per = (B + kMaxChunks - 1) / kMaxChunks;          // scenes per chunk (1 unless B > 32)
     int chunk = 0;
     for (int b0 = 0; b0 < B; b0 += per, ++chunk) {
         const int nb = (b0 + per <= B) ? per : (B - b0);
         MVF_TRY(cudaMemcpyAsync(w.feats + b0 * feat_scene, h_feats + b0 * feat_scene, nb * feat_scene * sizeof(float),
-                                cudaMemcpyHostToDevice, ax->sc));
+                                cudaMemcpyHostToDevice, ax->sh));
+        MVF_TRY(cudaEventRecord(ax->ev_in[chunk], ax->sh));
+        MVF_TRY(cudaStreamWaitEvent(ax->sc, ax->ev_in[chunk], 0));
         int rc = mvf_unproject_fuse(w.feats + b0 * feat_scene, w.Rcam + (size_t)b0 * V * 12, nullptr, w.Kmat + (size_t)b0 * 9, g,
                                     nb, V, fh, fw, C, img_h, img_w, mode, flags & ~MVF_FLAG_WORLD_GRID, 0.0, 0, 0,
                                     d_bn_scale, d_bn_shift, w.grid + b0 * grid_scene, nullptr, nullptr, nullptr, ax->sc);
         if (rc != MVF_OK) return rc;
-        rc = mvf_project_rays(w.grid + b0 * grid_scene, w.R0 + (size_t)b0 * 12, nullptr, w.Kmat + (size_t)b0 * 9, nullptr, g,
-                              nb, C, img_h, proj_h, proj_w, samples, 0, 0.0, 0, 0, w.out + b0 * out_scene, nullptr, nullptr, ax->sc);
+        if (col)
+            rc = mvf_project_depth_collapse(w.grid + b0 * grid_scene, w.R0 + (size_t)b0 * 12, nullptr, w.Kmat + (size_t)b0 * 9, nullptr, g,
+                                            nb, C, img_h, proj_h, proj_w, samples, MVF_FLAG_RELU_OUT, 0.0, 0, 0,
+                                            col->d_w, col->bias, col->bn_scale, col->bn_shift, w.out + b0 * out_scene, ax->sc);
+        else
+            rc = mvf_project_rays(w.grid + b0 * grid_scene, w.R0 + (size_t)b0 * 12, nullptr, w.Kmat + (size_t)b0 * 9, nullptr, g,
+                                  nb, C, img_h, proj_h, proj_w, samples, 0, 0.0, 0, 0, w.out + b0 * out_scene, nullptr, nullptr, ax->sc);
         if (rc != MVF_OK) return rc;
         MVF_TRY(cudaEventRecord(ax->ev[chunk], ax->sc));
         MVF_TRY(cudaStreamWaitEvent(ax->sd, ax->ev[chunk], 0));
@@ -131,4 +147,30 @@ extern "C" int mvf_unproject_fuse_project_host(const float* h_feats, const float
     MVF_TRY(cudaStreamSynchronize(s));
 #undef MVF_TRY
     return MVF_OK;
+}
+
+extern "C" int mvf_unproject_fuse_project_host(const float* h_feats, const float* h_Rcam, const float* h_Kmat,
+                                               const MvfGrid* g, int B, int V, int fh, int fw, int C,
+                                               int img_h, int img_w, int mode, int flags,
+                                               const float* d_bn_scale, const float* d_bn_shift,
+                                               int proj_h, int proj_w, int samples,
+                                               float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream) {
+    return host_pipeline(h_feats, h_Rcam, h_Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, d_bn_scale, d_bn_shift,
+                         proj_h, proj_w, samples, nullptr, h_out, dev_ws, dev_ws_bytes, stream);
+}
+
+// One pyramid level of the fusion neck (model_multi.py:2382-2404) from HOST buffers: unproj_feat -> grid_reas(sum|mean|max
+// [+BN+ReLU]) -> proj_grid -> depth_sampling (non-conv3d branch), i.e. features in, PG [B,P,P,C] out -- neither the fused
+// grid nor the ray slices cross the bus.  d_depth_w [S] device; the scalars are the folded depth conv bias / BN.
+extern "C" int mvf_fusion_neck_level_host(const float* h_feats, const float* h_Rcam, const float* h_Kmat,
+                                          const MvfGrid* g, int B, int V, int fh, int fw, int C,
+                                          int img_h, int img_w, int mode, int flags,
+                                          const float* d_bn_scale, const float* d_bn_shift,
+                                          int proj_h, int proj_w, int samples,
+                                          const float* d_depth_w, float depth_bias, float depth_bn_scale, float depth_bn_shift,
+                                          float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream) {
+    if (!d_depth_w) return MVF_ENULL;
+    const Collapse col = {d_depth_w, depth_bias, depth_bn_scale, depth_bn_shift};
+    return host_pipeline(h_feats, h_Rcam, h_Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, d_bn_scale, d_bn_shift,
+                         proj_h, proj_w, samples, &col, h_out, dev_ws, dev_ws_bytes, stream);
 }

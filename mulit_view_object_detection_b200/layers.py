@@ -828,7 +828,10 @@ class HostPipeline:
     ``keras_model.predict``, model_multi.py:3067-3068): pinned feats/Rcam/Kmat in, pinned ray slices
     out, device scratch owned by this object.  One call = H2D + K1 + K3 + D2H + stream sync."""
 
-    def __init__(self, config, B, V, fh, fw, Cc, proj_size, mode="sum", device=None):
+    def __init__(self, config, B, V, fh, fw, Cc, proj_size, mode="sum", device=None, depth=None, bn=None, relu_out=False):
+        """``depth`` = the depth_sampling learnables ({'weight' [S], 'bias', 'bn'}): the call then returns one level of the
+        fusion neck, PG [B,P,P,C] (``mvf_fusion_neck_level_host``), instead of the ray slices; ``bn`` / ``relu_out``: the
+        grid_reas BatchNorm + ReLU fused into K1."""
         self.config = config
         self.g = grid_from_config(config)
         self.shape = (B, V, fh, fw, Cc)
@@ -839,11 +842,15 @@ class HostPipeline:
         self.nbytes = lib.mvf_pipeline_host_workspace_bytes(C.byref(self.g), B, V, fh, fw, Cc, self.ph, self.pw, self.S)
         self.ws = torch.empty((self.nbytes,), dtype=torch.uint8, device=device)
         self.h2d_bytes = 4 * (B * V * fh * fw * Cc + B * V * 12 + B * 9)
-        self.d2h_bytes = 4 * B * self.S * self.ph * self.pw * Cc
+        self.depth = _depth_params("depth", depth, self.S, device) if depth is not None else None
+        self.bn = _bn_affine(bn, Cc, device)
+        self.flags = _lib.FLAG_RELU_OUT if relu_out else 0
+        self.d2h_bytes = 4 * B * (1 if self.depth else self.S) * self.ph * self.pw * Cc
 
     def empty_output(self):
         B, _, _, _, Cc = self.shape
-        return torch.empty((B, self.S, self.ph, self.pw, Cc), dtype=torch.float32).pin_memory()
+        shape = (B, self.ph, self.pw, Cc) if self.depth else (B, self.S, self.ph, self.pw, Cc)
+        return torch.empty(shape, dtype=torch.float32).pin_memory()
 
     def __call__(self, h_feats, h_Rcam, h_Kmat, h_out):
         for t, n in ((h_feats, "feats"), (h_Rcam, "Rcam"), (h_Kmat, "Kmat"), (h_out, "out")):
@@ -853,8 +860,16 @@ class HostPipeline:
         if tuple(h_feats.shape) != self.shape:
             raise ValueError("feats shape %s != %s" % (tuple(h_feats.shape), self.shape))
         ih, iw = _image_hw(self.config)
+        if self.depth:
+            w, bias, inv, shift = self.depth
+            rc = lib.mvf_fusion_neck_level_host(_ptr(h_feats), _ptr(h_Rcam), _ptr(h_Kmat), C.byref(self.g), B, V, fh, fw, Cc,
+                                                ih, iw, self.mode, self.flags, _ptr(self.bn[0]), _ptr(self.bn[1]),
+                                                self.ph, self.pw, self.S, _ptr(w), bias, inv, shift,
+                                                _ptr(h_out), _ptr(self.ws), self.nbytes, _stream())
+            check(rc, "mvf_fusion_neck_level_host")
+            return h_out
         rc = lib.mvf_unproject_fuse_project_host(_ptr(h_feats), _ptr(h_Rcam), _ptr(h_Kmat), C.byref(self.g), B, V, fh, fw, Cc,
-                                                 ih, iw, self.mode, 0, None, None, self.ph, self.pw, self.S,
-                                                 _ptr(h_out), _ptr(self.ws), self.nbytes, _stream())
+                                                 ih, iw, self.mode, self.flags, _ptr(self.bn[0]), _ptr(self.bn[1]),
+                                                 self.ph, self.pw, self.S, _ptr(h_out), _ptr(self.ws), self.nbytes, _stream())
         check(rc, "mvf_unproject_fuse_project_host")
         return h_out

@@ -268,3 +268,26 @@ def test_notebook_channel_mean():
         ref = oracle.channel_mean(g)
         assert tuple(out.shape) == ref.shape
         close(out.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_neck_level_host_entry_matches_device_path():
+    """mvf_fusion_neck_level_host: pinned features in, PG [B,P,P,C] out == unproject_fuse(+BN+ReLU) -> proj_grid_depth_sampling."""
+    import mulit_view_object_detection_b200 as m
+    rng = np.random.default_rng(4)
+    B, V, C, S, P = 3, 4, 64, 6, 20
+    cfg = small_cfg(nvox=16, nvox_z=16, samples=S, NUM_VIEWS=V)
+    feats, Rcam, Kmat = scene(cfg, B, V, 24, 24, C, seed=9)
+    bn = random_bn(rng, C)
+    depth = {"weight": rng.normal(0.1, 0.3, S).astype(np.float32), "bias": 0.03, "bn": (1.1, 0.02, -0.01, 0.9)}
+    pipe = m.HostPipeline(cfg, B, V, 24, 24, C, P, mode="sum", depth=depth, bn=bn, relu_out=True)
+    h_in = [torch.from_numpy(a).pin_memory() for a in (feats, Rcam, Kmat)]
+    h_out = pipe.empty_output()
+    assert tuple(h_out.shape) == (B, P, P, C)
+    pipe(h_in[0], h_in[1], h_in[2], h_out)
+    d = to_dev(feats, Rcam, Kmat)
+    fused = m.unproject_fuse(*d, cfg, mode="sum", bn=bn, relu_out=True)
+    ref = m.proj_grid_depth_sampling([fused, d[1], d[2]], cfg, P, "depth", params=depth)
+    assert torch.equal(h_out, ref.cpu())
+    o_fused = oracle.grid_reas(oracle.unproj_feat(feats, Rcam, Kmat, cfg), "g", small_cfg(GRID_REAS="add"), {"bn": bn})
+    o = oracle.depth_sampling(oracle.proj_grid(o_fused, Rcam, Kmat, cfg, P), depth["weight"], depth["bias"], depth["bn"])
+    close(h_out.numpy(), o, rtol=1e-5, atol=2e-6)
