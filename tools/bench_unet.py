@@ -70,3 +70,26 @@ res["depth_sampling_conv3d"] = {"ms": ms, "useful_tflops": fl / ms / 1e9}
 print("depth_sampling conv3d branch (S=%d, P=%d): %.3f ms  %.1f TFLOP/s useful" % (S, P, ms, fl / ms / 1e9))
 if len(sys.argv) > 3:
     json.dump(res, open(sys.argv[3], "w"), indent=1)
+
+# ---- one level of the conv3d neck end to end (model_multi.py:2382-2404 with GRID_REAS='conv3d'): unproj_feat (per-view grids) ->
+# U-Net -> proj_grid -> depth_sampling conv3d branch, device resident
+import numpy as np
+from mulit_view_object_detection_b200 import synthetic as syn
+cfg = m.FusionConfig(nvox=X, nvox_z=X, samples=S, NUM_VIEWS=V, GRID_REAS="conv3d", IMAGE_SHAPE=np.array([640, 640, 3]),
+                     TOP_DOWN_PYRAMID_SIZE=F, VANILLA=True)
+feats, Rcam, Kmat = syn.make_scene(cfg, 1, V, P, P, C, seed=5)
+d = [torch.from_numpy(a).to(dev) for a in (feats, Rcam, Kmat)]
+wl = lambda *shape, fan: rnd(*shape, scale=fan ** -0.5)
+nparams = {"grid_reas_P4": {"conv1": {"W": wl(3, 3, 3, V * C, 2 * F, fan=27 * V * C), "b": rnd(2 * F, scale=0.1)},
+                            "conv2": {"W": wl(3, 3, 3, 2 * F, 4 * F, fan=27 * 2 * F), "b": rnd(4 * F, scale=0.1)},
+                            "deconv1": {"W": wl(3, 3, 3, 2 * F, 4 * F, fan=8 * 4 * F), "b": rnd(2 * F, scale=0.1)},
+                            "deconv2": {"W": wl(3, 3, 3, F, 4 * F, fan=8 * 4 * F), "b": rnd(F, scale=0.1)}},
+           "grid_reas_depth_PG4": params}
+ms_k1, per_view = timed(lambda: m.unproj_feat(d, cfg))
+ms_neck, pg = timed(lambda: m.fusion_neck([d[0]], d[1], d[2], cfg, params=nparams, levels=(4,)))
+res["k1_none_ms"] = ms_k1
+res["neck_conv3d_P4_ms"] = ms_neck
+print("unproj_feat (per-view grids, %.2f GB): %.3f ms = %.0f GB/s written;  conv3d neck level P4 end to end: %.3f ms  -> PG %s"
+      % (per_view.numel() * 4 / 1e9, ms_k1, per_view.numel() * 4 / ms_k1 / 1e6, ms_neck, tuple(pg[0].shape)))
+if len(sys.argv) > 3:
+    json.dump(res, open(sys.argv[3], "w"), indent=1)
