@@ -101,3 +101,51 @@ def test_random_roi_align(seed, R, pool, c4):
     got, lv = m.PyramidROIAlign(pool)([to_dev(boxes)[0], meta] + to_dev(*maps), return_levels=True)
     assert np.array_equal(lv.cpu().numpy(), oracle.roi_levels(boxes, (96, 96, 3)))
     assert np.array_equal(got.cpu().numpy(), oracle.pyramid_roi_align(boxes, (96, 96, 3), maps, pool))     # bit-exact crops
+
+
+@st.composite
+def conv_cases(draw):
+    kind = draw(st.sampled_from(["conv1", "conv3", "conv_s2", "deconv_s2"]))
+    B, V = draw(st.integers(1, 2)), draw(st.integers(1, 3))
+    C = 32 * draw(st.integers(1, 4))                       # 32 / 96: tf32 split, 64 / 128: fp16 split
+    C2 = draw(st.sampled_from([0, 0, C]))
+    Cout = 16 * draw(st.integers(1, 20))                   # not a multiple of the 256-column tile: ragged N
+    dims = [draw(st.integers(1, 5)) for _ in range(3)]
+    if kind == "conv_s2":
+        dims = [2 * d for d in dims]
+    return kind, B, V, C, C2, Cout, dims, draw(st.integers(0, 2 ** 31 - 1)), draw(st.booleans())
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(conv_cases())
+def test_random_tensor_core_convolutions(case):
+    """mvf_conv3d_tc over random kinds / shapes / channel counts (both operand-split formats, ragged tiles, several view
+    sources, the skip-concat second source) against the oracle's Conv3D / Conv3DTranspose."""
+    m = _m()
+    kind, B, V, C, C2, Cout, (X, Y, Z), seed, relu_in = case
+    rng = np.random.default_rng(seed)
+    Cin = V * C + C2
+    k = 1 if kind == "conv1" else 3
+    fan = (8 if kind == "deconv_s2" else k ** 3) * Cin
+    wshape = (k, k, k, Cout, Cin) if kind == "deconv_s2" else (k, k, k, Cin, Cout)
+    W = (rng.standard_normal(wshape) / np.sqrt(fan)).astype(np.float32)
+    b = rng.normal(0, 0.1, Cout).astype(np.float32)
+    x = rng.standard_normal((B, V, X, Y, Z, C)).astype(np.float32)
+    x2 = rng.standard_normal((B, X, Y, Z, C2)).astype(np.float32) if C2 else None
+    lkind = {"conv1": "conv", "conv3": "conv"}.get(kind, kind)
+    conv = m.Conv3dTensorCore(*to_dev(W, b), lkind, V=V, C2=C2)
+    got = conv(to_dev(x)[0], x2=to_dev(x2)[0] if C2 else None, relu_in=relu_in, relu_out=False).cpu().numpy()
+    xin = np.transpose(x, (0, 2, 3, 4, 1, 5)).reshape(B, X, Y, Z, V * C)
+    if C2:
+        xin = np.concatenate([xin, x2], axis=-1)
+    if relu_in:
+        xin = np.maximum(xin, 0)
+    if kind == "conv_s2":
+        ref = oracle.conv3d_strided_same(xin, W, 2)
+    elif kind == "deconv_s2":
+        ref = oracle.conv3d_transpose_same(xin, W, 2)
+    else:
+        ref = oracle.fusion.conv3d_same(xin, W)
+    ref = (ref + b).astype(np.float32)
+    assert got.shape == ref.shape
+    close(got, ref, rtol=1e-5, atol=5e-6)
