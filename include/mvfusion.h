@@ -124,6 +124,8 @@ int mvf_ident_fuse(const float* in, const float* weight, const float* bias,
  *     while `in` supplies S sources of C channels (depth_sampling, :468-470).
  * ws: mvf_conv3d_tc_workspace_bytes(...) bytes of device scratch for the hi/lo halves of the activations -- 0 (ws may be
  *     NULL) when the split is fused into the GEMM, which the library chooses for large 1x1x1 convolutions.
+ * act_amax: NULL, or a DEVICE pointer to an upper bound of max|in|, |in2| (after the optional ReLU) for the fp16 operand scale;
+ *     saves the max-reduction pass when the caller knows one (unprojected grids are bounded by max|features|).
  * Needs C % 32 == 0, C2 % 32 == 0, Cout % 16 == 0 (MVF_EUNSUPPORTED otherwise). */
 #define MVF_CONV_S1   0
 #define MVF_CONV_S2   1
@@ -135,7 +137,7 @@ size_t mvf_conv3d_tc_workspace_bytes(int kind, int ksize, int B, int V, int X, i
 int mvf_conv3d_tc(const float* in, const float* in2, const float* wsplit, const float* bias,
                   const float* bn_scale, const float* bn_shift, const float* pre_scale, const float* pre_shift,
                   int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout, int flags,
-                  float* out, void* ws, size_t ws_bytes, void* stream);
+                  float* out, void* ws, size_t ws_bytes, const float* act_amax, void* stream);
 
 /* ---- grid_reas 'ident' on the tensor cores (tcgen05, 3xTF32 split) ------------------------------
  * Same contract as mvf_ident_fuse (model_multi.py:443-455) for C % 32 == 0 and Cout % 16 == 0

@@ -53,7 +53,7 @@ _SIGS = {
     "mvf_conv3d_wsplit_bytes": (_sz, [_i, _i, _i, _i]),
     "mvf_conv3d_prepare": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "mvf_conv3d_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
-    "mvf_conv3d_tc": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "mvf_conv3d_tc": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p, _p]),
     "mvf_ident_wsplit_bytes": (_sz, [_i, _i, _i]),
     "mvf_ident_prepare": (_i, [_p, _i, _i, _i, _p, _p]),
     "mvf_ident_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),

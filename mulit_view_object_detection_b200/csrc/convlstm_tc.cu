@@ -846,7 +846,7 @@ extern "C" size_t mvf_conv3d_tc_workspace_bytes(int kind, int ksize, int B, int 
 extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsplit, const float* bias,
                              const float* bn_scale, const float* bn_shift, const float* pre_scale, const float* pre_shift,
                              int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout, int flags,
-                             float* out, void* ws, size_t ws_bytes, void* stream) {
+                             float* out, void* ws, size_t ws_bytes, const float* act_amax, void* stream) {
     if (!in || !wsplit || !bias || !out) return MVF_ENULL;
     if ((bn_scale == nullptr) != (bn_shift == nullptr) || (pre_scale == nullptr) != (pre_shift == nullptr)) return MVF_ENULL;
     if ((in2 == nullptr) != (C2 == 0)) return MVF_EINVAL;
@@ -870,12 +870,17 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     if (f16) {
         __half* w0 = (__half*)ws; __half* w1 = w0 + n1; __half* w2 = w1 + n1; __half* w3 = w2 + n2;
         unsigned* tail = (unsigned*)(((uintptr_t)(w3 + n2) + 15) & ~(uintptr_t)15);
-        if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
-        amax_kernel<<<amax_grid(n1 / 4), 256, 0, s>>>((const float4*)in, n1 / 4, relu_in, tail);
-        if (in2) amax_kernel<<<amax_grid(n2 / 4), 256, 0, s>>>((const float4*)in2, n2 / 4, relu_in, tail);      // sources share the accumulator: one scale
+        if (act_amax) {                                  // the caller's bound on max|operand| (e.g. max|features| for unprojected grids)
+            if (cudaMemcpyAsync(tail, act_amax, 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return MVF_ECUDA;
+        } else {
+            if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
+            amax_kernel<<<amax_grid(n1 / 4), 256, 0, s>>>((const float4*)in, n1 / 4, relu_in, tail);
+            if (in2) amax_kernel<<<amax_grid(n2 / 4), 256, 0, s>>>((const float4*)in2, n2 / 4, relu_in, tail);  // sources share the accumulator: one scale
+            count_launch(in2 ? 2 : 1);
+        }
         act_split_f16_kernel<<<(unsigned)((n1 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (uint2*)w0, (uint2*)w1, n1 / 4, X, Y, Z, C / 4, relu_in, s2d, tail);
         if (in2) act_split_f16_kernel<<<(unsigned)((n2 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in2, (uint2*)w2, (uint2*)w3, n2 / 4, X, Y, Z, C2 / 4, relu_in, s2d, tail);
-        count_launch(in2 ? 4 : 2);
+        count_launch(in2 ? 2 : 1);
         xh = w0; xl = w1; hh = w2; hl = w3;
         inv_a = (const float*)tail + 1;
     } else if (split_pass) {
@@ -956,5 +961,5 @@ extern "C" int mvf_ident_fuse_tc(const float* in, const float* wsplit, const flo
                                  int B, int V, int X, int Y, int Z, int C, int Cout,
                                  float* out, void* ws, size_t ws_bytes, void* stream) {
     return mvf_conv3d_tc(in, nullptr, wsplit, bias, bn_scale, bn_shift, nullptr, nullptr, MVF_CONV_S1, 1, B, V, X, Y, Z, C, 0, Cout,
-                         MVF_FLAG_RELU_IN | MVF_FLAG_RELU_OUT, out, ws, ws_bytes, stream);
+                         MVF_FLAG_RELU_IN | MVF_FLAG_RELU_OUT, out, ws, ws_bytes, nullptr, stream);
 }

@@ -376,9 +376,10 @@ class Conv3dTensorCore:
             return 2 * X, 2 * Y, 2 * Z
         return X, Y, Z
 
-    def __call__(self, x, x2=None, relu_in=False, relu_out=True, pre=None):
+    def __call__(self, x, x2=None, relu_in=False, relu_out=True, pre=None, act_amax=None):
         """x [B,V,X,Y,Z,C] (or [B,X,Y,Z,C] when V == 1); x2 [B,X,Y,Z,C2] appended on channels; ``pre`` = (scale, shift)
-        per input channel [V*C] applied before the conv (a depthwise 1x1)."""
+        per input channel [V*C] applied before the conv (a depthwise 1x1); ``act_amax``: 1-element device tensor bounding
+        max|x|, |x2| (skips the max-reduction pass of the fp16 operand split)."""
         x = _cuda(x, "x")
         if x.dim() == 5:
             x = x.unsqueeze(1)
@@ -401,7 +402,8 @@ class Conv3dTensorCore:
         flags = (_lib.FLAG_RELU_IN if relu_in else 0) | (_lib.FLAG_RELU_OUT if relu_out else 0)
         rc = lib.mvf_conv3d_tc(_ptr(x), _ptr(x2), _ptr(self.wsplit), _ptr(self.bias), _ptr(self.scale), _ptr(self.shift),
                                _ptr(ps), _ptr(psh), self.kind, self.ksize, B, V, X, Y, Z, Cc, self.C2, self.Cout, flags,
-                               _ptr(out), _ptr(self._ws) if need else None, self._ws.numel() * 4 if need else 0, _stream())
+                               _ptr(out), _ptr(self._ws) if need else None, self._ws.numel() * 4 if need else 0,
+                               _ptr(act_amax), _stream())
         check(rc, "mvf_conv3d_tc")
         return out
 
@@ -419,7 +421,7 @@ def _cached_conv(name, p, kind, **kw):
     return hit[1]
 
 
-def unet_fuse(x, scope, config, params):
+def unet_fuse(x, scope, config, params, act_amax=None):
     """``GRID_REAS='conv3d'`` (model_multi.py:406-441): the MLF U-Net over the view-concatenated grids, four tensor-core
     convolutions; the per-view grids [B,V,X,Y,Z,C] are consumed in place (no transpose / reshape / concat copies)."""
     x = _cuda(x, "inputs")
@@ -427,7 +429,7 @@ def unet_fuse(x, scope, config, params):
     if X % 4 or Y % 4 or Z % 4:
         raise ValueError("the conv3d U-Net halves the grid twice: nvox and nvox_z must be multiples of 4")
     name = scope + "_3D_conv"
-    conv1 = _cached_conv(name + "_1", params["conv1"], "conv_s2", V=V)(x, relu_in=True)               # :415-421
+    conv1 = _cached_conv(name + "_1", params["conv1"], "conv_s2", V=V)(x, relu_in=True, act_amax=act_amax)   # :415-421
     conv2 = _cached_conv(name + "_2", params["conv2"], "conv_s2")(conv1)                                # :423-428
     deconv1 = _cached_conv(name + "_deconv_1", params["deconv1"], "deconv_s2")(conv2)                   # :430-436
     C2 = conv1.shape[-1]
@@ -475,7 +477,7 @@ def convlstm(grid, name, kernel=(3, 3, 3), filters=32, params=None, relu_in=Fals
     return h
 
 
-def grid_reas(inputs, scope, config, kernel=(3, 3, 3), params=None, tensor_cores=None):
+def grid_reas(inputs, scope, config, kernel=(3, 3, 3), params=None, tensor_cores=None, act_amax=None):
     """``grid_reas(inputs, scope, config)`` (model_multi.py:394-463) on a materialised
     [B,V,X,Y,Z,C] tensor; modes add | mean | max | ident | lstm3d."""
     x = _cuda(inputs, "inputs")
@@ -507,7 +509,7 @@ def grid_reas(inputs, scope, config, kernel=(3, 3, 3), params=None, tensor_cores
         check(rc, "mvf_ident_fuse")
         return out
     if mode == "conv3d":
-        return unet_fuse(x, scope, config, p)
+        return unet_fuse(x, scope, config, p, act_amax=act_amax)
     if mode == "lstm3d":
         h = convlstm(x, scope + "_convlstm3d", kernel=kernel, filters=config.TOP_DOWN_PYRAMID_SIZE,
                      params={"W": p["W"], "b": p["b"]} if "W" in p else None, relu_in=True)
@@ -665,7 +667,10 @@ def fusion_neck(feature_maps, Rcam, Kmat, config, params=None, levels=(2, 3, 4, 
             outs.append(proj_grid_depth_sampling([fused, Rcam, Kmat], config, P_, dname, params=dp))
             continue
         per_view = unproj_feat([fm, Rcam, Kmat], config)
-        fused = grid_reas(per_view, gname, config, params=gp)
+        # bilinear weights are in [0,1] and sum to at most 1, so the unprojected grids are bounded by max|features|: the U-Net's
+        # first conv takes its fp16 operand scale from this (tiny) reduction instead of a pass over the 2 GB of grids
+        bound = fm.abs().amax().reshape(1) if config.GRID_REAS == "conv3d" else None
+        fused = grid_reas(per_view, gname, config, params=gp, act_amax=bound)
         del per_view
         rays = proj_grid([fused, Rcam, Kmat], config, P_)
         outs.append(depth_sampling(rays, config, dname, params=dp))

@@ -139,3 +139,35 @@ def test_fp16_split_keeps_fp32_accuracy_over_a_wide_dynamic_range():
     got_s = conv0(to_dev(xs)[0], relu_out=False).cpu().numpy()
     ref_s = oracle.fusion.conv3d_same(xs, p["W"]).astype(np.float32)
     assert np.abs(got_s - ref_s).max() <= 1e-5 * float(np.abs(ref_s).max())
+
+
+def test_fusion_neck_conv3d_mode():
+    """The shipped configuration (GRID_REAS='conv3d', interior_multi.py:391,419) through fusion_neck: unproj_feat -> U-Net ->
+    proj_grid -> depth_sampling conv3d branch, fp16-rate convolutions with the operand scale bounded by max|features|."""
+    m = _m()
+    from helpers import scene
+    rng = np.random.default_rng(21)
+    B, V, C, F, S = 1, 2, 64, 64, 4
+    cfg = small_cfg(GRID_REAS="conv3d", NUM_VIEWS=V, nvox=8, nvox_z=8, samples=S, TOP_DOWN_PYRAMID_SIZE=F,
+                    IMAGE_SHAPE=np.array([128, 128, 3]), VANILLA=True)
+    levels = (4, 5)
+    fmaps = []
+    for lvl in levels:
+        f, Rcam, Kmat = scene(cfg, B, V, 128 >> lvl, 128 >> lvl, C, seed=6, image_hw=(128, 128))
+        fmaps.append(f)
+    params = {}
+    for lvl in levels:
+        params["grid_reas_P%d" % lvl] = {"conv1": _layer(rng, (3, 3, 3, V * C, 2 * F), 27 * V * C, 2 * F),
+                                         "conv2": _layer(rng, (3, 3, 3, 2 * F, 4 * F), 27 * 2 * F, 4 * F),
+                                         "deconv1": _layer(rng, (3, 3, 3, 2 * F, 4 * F), 8 * 4 * F, 2 * F),
+                                         "deconv2": _layer(rng, (3, 3, 3, F, 4 * F), 8 * 4 * F, F)}
+        params["grid_reas_depth_PG%d" % lvl] = {
+            "dw1": {"w": rng.uniform(0.5, 1.5, F * S).astype(np.float32), "b": rng.normal(0, 0.1, F * S).astype(np.float32)},
+            "conv1": _layer(rng, (F * S, 64), F * S, 64),
+            "dw2": {"w": rng.uniform(0.5, 1.5, 64).astype(np.float32), "b": rng.normal(0, 0.1, 64).astype(np.float32)},
+            "conv2": _layer(rng, (64, F), 64, F)}
+    outs = m.fusion_neck(to_dev(*fmaps), *to_dev(Rcam, Kmat), cfg, params=m.prepare_params(params), levels=levels)
+    refs = oracle.fusion_neck(fmaps, Rcam, Kmat, cfg, params, levels=levels)
+    for o, r in zip(outs, refs):
+        assert tuple(o.shape) == r.shape
+        close(o.cpu().numpy(), r, rtol=1e-5, atol=5e-6)
