@@ -21,6 +21,9 @@ TensorFlow 1.x + Keras 2.x, which are not installable here.  What pins this orac
   build container) over a small eager NumPy stand-in for the ``tf`` namespace, and stores
   inputs/outputs as fixtures under ``tests/golden/``.  That pins every reference-authored
   decision (operand order, transposes, meshgrid order, index layout, gate order ...).
+  ``grid_reas`` ('add', 'ident', 'conv3d') and ``depth_sampling`` (both branches) -- Keras graph builders -- are executed
+  with functional stand-ins for the layers they instantiate, weights looked up by the reference's layer names: that pins the
+  wiring (channel orders, ReLU placement, skip-concat order, names), not the Keras kernels inside the layers.
 * the pure-NumPy helpers of the reference (``mrcnn/utils.py``: ``compute_iou``,
   ``non_max_suppression``, ``apply_box_deltas``, ``vec2rot``, ``quat2rot``) run unmodified.
 * The third-party TensorFlow kernels themselves (``gather_nd`` out-of-range behaviour,

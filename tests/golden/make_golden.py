@@ -195,7 +195,162 @@ def gen_poses():
          vec=vec, vec_R=np.stack([ref_utils.vec2rot(x) for x in vec]))
 
 
+# ---- the reference's grid_reas / depth_sampling wiring (mrcnn/model_multi.py:394-488) -----------------------------------
+# These functions are Keras graph builders.  They are EXECUTED here with small functional stand-ins for the Keras layers
+# they instantiate (weights looked up by the layer NAME the reference gives them), so the fixtures pin everything the
+# reference authored: transposes / reshapes (view-major channel order, the c*S+s depth order), ReLU placement, layer
+# sequence, the skip-concat order and the layer names.  The arithmetic inside a stand-in layer is the oracle's
+# restatement of the Keras / TF kernel (third-party: unpinned, see oracle/__init__.py).
+import oracle  # noqa: E402
+
+LAYER_WEIGHTS = {}          # layer name -> get_weights() list, filled by the generators below
+
+
+class _Lambda:
+    def __init__(self, fn, name=None, **k):
+        self.fn = fn
+
+    def __call__(self, x):
+        return self.fn(x)
+
+
+class _Activation:
+    def __init__(self, kind, **k):
+        assert kind == "relu"
+
+    def __call__(self, x):
+        return T(np.maximum(arr(x), np.float32(0)))
+
+
+class _Conv3D:
+    def __init__(self, filters, kernel_size, strides=(1, 1, 1), padding="valid", name=None, **k):
+        assert padding == "same"
+        self.name, self.stride, self.filters = name, int(strides[0]), filters
+
+    def __call__(self, x):
+        W, b = LAYER_WEIGHTS[self.name]
+        assert W.shape[-1] == self.filters
+        return T((oracle.conv3d_strided_same(arr(x), W, self.stride) + b.astype(np.float64)).astype(np.float32))
+
+
+class _Conv3DTranspose(_Conv3D):
+    def __call__(self, x):
+        W, b = LAYER_WEIGHTS[self.name]
+        assert W.shape[-2] == self.filters
+        return T((oracle.conv3d_transpose_same(arr(x), W, self.stride) + b.astype(np.float64)).astype(np.float32))
+
+
+class _TimeDistributed:
+    """KL.TimeDistributed(BatchNorm(), name) (add_bn_layer, :501-502) and KL.TimeDistributed(KL.Conv2D(1,(1,1)), name) (:483)."""
+
+    def __init__(self, layer, name=None, **k):
+        self.layer, self.name = layer, name
+
+    def __call__(self, x, training=None):
+        if isinstance(self.layer, _Conv2D):
+            return self.layer(x, name=self.name)
+        scale, shift = oracle.batch_norm_affine(*LAYER_WEIGHTS[self.name])
+        return T(arr(x) * scale + shift)
+
+
+class _Conv2D:
+    def __init__(self, filters, kernel_size, padding="valid", name=None, **k):
+        assert tuple(kernel_size) == (1, 1)
+        self.name, self.filters = name, filters
+
+    def __call__(self, x, name=None):
+        W, b = LAYER_WEIGHTS[name or self.name]
+        W = np.asarray(W).reshape(W.shape[-2], W.shape[-1])
+        return T((arr(x).astype(np.float64) @ W.astype(np.float64)).astype(np.float32) + b)
+
+
+class _DepthwiseConv2D:
+    def __init__(self, kernel_size, depth_multiplier=1, name=None, **k):
+        assert tuple(kernel_size) == (1, 1) and depth_multiplier == 1
+        self.name = name
+
+    def __call__(self, x):
+        w, b = LAYER_WEIGHTS[self.name]
+        return T(arr(x) * np.asarray(w).reshape(-1) + b)
+
+
+def _install_layers():
+    KL = mm.KL
+    KL.Lambda, KL.Activation, KL.Conv3D, KL.Conv3DTranspose = _Lambda, _Activation, _Conv3D, _Conv3DTranspose
+    KL.TimeDistributed, KL.Conv2D, KL.DepthwiseConv2D = _TimeDistributed, _Conv2D, _DepthwiseConv2D
+    tf.keras.backend.sum = lambda x, axis=None: T(np.sum(arr(x), axis=axis, dtype=np.float32))
+
+
+def _rand_bn(rng, n):
+    return [rng.uniform(0.8, 1.2, n).astype(np.float32), rng.normal(0, 0.05, n).astype(np.float32),
+            rng.normal(0, 0.05, n).astype(np.float32), rng.uniform(0.7, 1.3, n).astype(np.float32)]
+
+
+def _flat(named):
+    return {"w__%s__%d" % (k, i): np.asarray(a) for k, ws in named.items() for i, a in enumerate(ws)}
+
+
+def gen_grid_reas():
+    _install_layers()
+    rng = np.random.default_rng(18)
+    B, V, X, Z, C, F = 1, 3, 4, 8, 4, 4
+    grids = rng.standard_normal((B, V, X, X, Z, C)).astype(np.float32)
+    scope = "grid_reas_P4"
+    for mode in ("add", "ident", "conv3d", "conv3d_tc"):
+        if mode == "conv3d_tc":        # channel counts the tensor-core path accepts (32-channel K chunks), still a small file
+            V, C, F, mode = 1, 32, 16, "conv3d"
+            grids = rng.standard_normal((B, V, X, X, Z, C)).astype(np.float32)
+            tag = "conv3d_tc"
+        else:
+            tag = mode
+        cfg = FusionConfig(GRID_REAS=mode, NUM_VIEWS=V, nvox=X, nvox_z=Z, TOP_DOWN_PYRAMID_SIZE=F)
+        cfg.TRAIN_BN = False
+        LAYER_WEIGHTS.clear()
+        mm.reused_lay.clear()
+        if mode == "add":
+            LAYER_WEIGHTS[scope + "_batch_norm"] = _rand_bn(rng, C)
+        elif mode == "ident":
+            LAYER_WEIGHTS[scope + "ident_conv"] = [(rng.standard_normal((1, 1, 1, V * C, F)) * 0.3).astype(np.float32),
+                                                   rng.normal(0, 0.1, F).astype(np.float32)]
+            LAYER_WEIGHTS[scope + "_batch_norm"] = _rand_bn(rng, F)
+        else:
+            nc, nb = scope + "_3D_conv", scope + "_batch_norm"
+            for suf, bsuf, shp, nout in (("_1", "_1", (3, 3, 3, V * C, 2 * F), 2 * F), ("_2", "_2", (3, 3, 3, 2 * F, 4 * F), 4 * F),
+                                         ("_deconv_1", "deconv_1", (3, 3, 3, 2 * F, 4 * F), 2 * F),
+                                         ("_deconv_2", "deconv_2", (3, 3, 3, F, 4 * F), F)):
+                LAYER_WEIGHTS[nc + suf] = [(rng.standard_normal(shp) * 0.1).astype(np.float32), rng.normal(0, 0.1, nout).astype(np.float32)]
+                LAYER_WEIGHTS[nb + bsuf] = _rand_bn(rng, nout)
+        out = quiet(mm.grid_reas, T(grids), scope, cfg)
+        save("grid_reas_" + tag, grids=grids, out=arr(out), V=np.int32(V), F=np.int32(F), **_flat(LAYER_WEIGHTS))
+
+
+def gen_depth_sampling():
+    _install_layers()
+    rng = np.random.default_rng(19)
+    B, S, P, C, F = 2, 5, 3, 4, 4
+    x = np.maximum(rng.standard_normal((B, S, P, P, C)), 0).astype(np.float32)
+    name = "grid_reas_depth_PG4"
+    for mode in ("add", "conv3d"):
+        cfg = FusionConfig(GRID_REAS=mode, samples=S, TOP_DOWN_PYRAMID_SIZE=F)
+        cfg.TRAIN_BN = False
+        LAYER_WEIGHTS.clear()
+        if mode == "conv3d":
+            for i, (cin, cout) in enumerate(((C * S, 512), (512, F)), 1):
+                LAYER_WEIGHTS[name + "_DepthwiseConv_%d" % i] = [rng.uniform(0.5, 1.5, (1, 1, cin, 1)).astype(np.float32),
+                                                                 rng.normal(0, 0.1, cin).astype(np.float32)]
+                LAYER_WEIGHTS[name + "2DConv_%d" % i] = [(rng.standard_normal((1, 1, cin, cout)) * cin ** -0.5).astype(np.float32),
+                                                          rng.normal(0, 0.1, cout).astype(np.float32)]
+                LAYER_WEIGHTS[name + "bn_%d" % i] = _rand_bn(rng, cout)
+        else:
+            LAYER_WEIGHTS[name + "2DConv"] = [rng.normal(0.1, 0.3, (1, 1, S, 1)).astype(np.float32), np.array([0.05], np.float32)]
+            LAYER_WEIGHTS[name + "bn_deconv"] = _rand_bn(rng, 1)
+        out = quiet(mm.depth_sampling, T(x), cfg, name)
+        save("depth_sampling_" + mode, x=x, out=arr(out), S=np.int32(S), F=np.int32(F), **_flat(LAYER_WEIGHTS))
+
+
 if __name__ == "__main__":
+    gen_grid_reas()
+    gen_depth_sampling()
     gen_unproject_project()
     gen_boxes()
     gen_nms_utils()

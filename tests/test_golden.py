@@ -114,3 +114,64 @@ def test_pose_helpers_match_reference():
         np.testing.assert_allclose(syn.look_at_rotation(vec[:3], vec[3:6], vec[6:]), R, rtol=1e-12, atol=1e-12)
     for q, R in zip(d["quat"], d["quat_R"]):
         assert abs(np.linalg.det(R) - 1) < 1e-9 and np.allclose(R @ R.T, np.eye(3), atol=1e-9)
+
+
+# ---- the reference's grid_reas / depth_sampling WIRING (model_multi.py:394-488), executed with functional layer stand-ins
+def named_weights(d):
+    """{keras layer name: get_weights() list} as stored by make_golden.py (keys w__<layer>__<i>)."""
+    named = {}
+    for k in d.files:
+        if k.startswith("w__"):
+            _, layer, i = k.split("__")
+            named.setdefault(layer, {})[int(i)] = d[k]
+    return {k: [v[i] for i in sorted(v)] for k, v in named.items()}
+
+
+@pytest.mark.parametrize("mode", ["add", "ident", "conv3d", "conv3d_tc"])
+def test_grid_reas_wiring_and_layer_names(mode):
+    """Layer names -> parameters through weights_io (the names the reference gives its Keras layers), then the oracle's
+    grid_reas must reproduce what the reference's own grid_reas computed: view-major channel order, ReLU placement, the
+    deconv-first skip concat, the BN layer names without underscore."""
+    from mulit_view_object_detection_b200 import weights_io as wio
+    d = load("grid_reas_" + mode)
+    mode = mode.split("_")[0]
+    V, F = int(d["V"]), int(d["F"])
+    cfg = FusionConfig(GRID_REAS=mode, NUM_VIEWS=V, nvox=d["grids"].shape[2], nvox_z=d["grids"].shape[4], TOP_DOWN_PYRAMID_SIZE=F)
+    named = named_weights(d)
+    named.update({"grid_reas_depth_PG4" + s: w for s, w in _dummy_depth(cfg, F).items()})
+    params = wio.fusion_params_from_keras(named, cfg, levels=(4,))["grid_reas_P4"]
+    out = oracle.grid_reas(d["grids"], "grid_reas_P4", cfg, params)
+    assert out.shape == d["out"].shape
+    np.testing.assert_allclose(out, d["out"], rtol=2e-6, atol=2e-7)
+
+
+def _dummy_depth(cfg, F):
+    S = int(cfg.samples)
+    one = [np.ones(1, np.float32), np.zeros(1, np.float32), np.zeros(1, np.float32), np.ones(1, np.float32)]
+    if cfg.GRID_REAS == "conv3d":
+        out = {}
+        for i, (cin, cout) in enumerate(((F * S, 8), (8, F)), 1):
+            out["_DepthwiseConv_%d" % i] = [np.ones((1, 1, cin, 1), np.float32), np.zeros(cin, np.float32)]
+            out["2DConv_%d" % i] = [np.zeros((1, 1, cin, cout), np.float32), np.zeros(cout, np.float32)]
+        return out
+    return {"2DConv": [np.zeros((1, 1, S, 1), np.float32), np.zeros(1, np.float32)], "bn_deconv": one}
+
+
+@pytest.mark.parametrize("mode", ["add", "conv3d"])
+def test_depth_sampling_wiring_and_layer_names(mode):
+    from mulit_view_object_detection_b200 import weights_io as wio
+    d = load("depth_sampling_" + mode)
+    S, F = int(d["S"]), int(d["F"])
+    cfg = FusionConfig(GRID_REAS=mode, samples=S, TOP_DOWN_PYRAMID_SIZE=F, NUM_VIEWS=1)
+    named = named_weights(d)
+    if mode == "conv3d":                      # the grid_reas layers are not part of this fixture: placeholders for the mapper
+        for suf, shp, n in (("_1", (3, 3, 3, d["x"].shape[-1], 2 * F), 2 * F), ("_2", (3, 3, 3, 2 * F, 4 * F), 4 * F),
+                            ("_deconv_1", (3, 3, 3, 2 * F, 4 * F), 2 * F), ("_deconv_2", (3, 3, 3, F, 4 * F), F)):
+            named["grid_reas_P4_3D_conv" + suf] = [np.zeros(shp, np.float32), np.zeros(n, np.float32)]
+    p = wio.fusion_params_from_keras(named, cfg, levels=(4,))["grid_reas_depth_PG4"]
+    if mode == "conv3d":
+        out = oracle.depth_sampling_conv3d(d["x"], p)
+    else:
+        out = oracle.depth_sampling(d["x"], p["weight"], p["bias"], p.get("bn"))
+    assert out.shape == d["out"].shape
+    np.testing.assert_allclose(out, d["out"], rtol=2e-6, atol=2e-7)

@@ -83,3 +83,40 @@ def test_convlstm_vs_reference_cell():
         h, c = m.convlstm_step(to_dev(d["x"][:, t])[0], h, c, dW, db)
         close(h.cpu().numpy(), d["h"][:, t], rtol=1e-5, atol=2e-6)
         close(c.cpu().numpy(), d["c"][:, t], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("mode", ["add", "ident", "conv3d", "conv3d_tc"])
+def test_grid_reas_vs_reference_fixture(mode):
+    """The CUDA grid_reas against what the reference's own grid_reas computed (tests/golden/grid_reas_*.npz).  The tiny channel
+    counts of the first fixtures take the exact-fp32 kernels for 'ident' and are rejected by the tensor-core U-Net; the
+    'conv3d_tc' fixture has 32-channel sources and runs the U-Net on the tensor cores."""
+    m = _m()
+    from test_golden import named_weights, _dummy_depth
+    from mulit_view_object_detection_b200 import weights_io as wio
+    d = load("grid_reas_" + mode)
+    tiny = mode == "conv3d"
+    mode = mode.split("_")[0]
+    V, F = int(d["V"]), int(d["F"])
+    cfg = FusionConfig(GRID_REAS=mode, NUM_VIEWS=V, nvox=d["grids"].shape[2], nvox_z=d["grids"].shape[4], TOP_DOWN_PYRAMID_SIZE=F)
+    named = named_weights(d)
+    named.update({"grid_reas_depth_PG4" + s: w for s, w in _dummy_depth(cfg, F).items()})
+    params = wio.fusion_params_from_keras(named, cfg, levels=(4,))
+    if tiny:
+        with pytest.raises(ValueError):            # 12 -> 8 channels: below the 32-channel K chunk of the tensor-core path
+            m.grid_reas(to_dev(d["grids"])[0], "grid_reas_P4", cfg, params=m.prepare_params(params)["grid_reas_P4"])
+        return
+    out = m.grid_reas(to_dev(d["grids"])[0], "grid_reas_P4", cfg, params=m.prepare_params(params)["grid_reas_P4"])
+    # four chained convolutions with un-normalised random weights (gain > 1 per layer): 1e-5 relative, floor 2e-6 of the output scale
+    close(out.cpu().numpy(), d["out"], rtol=1e-5, atol=2e-6 * max(1.0, float(np.abs(d["out"]).max())))
+
+
+def test_depth_sampling_vs_reference_fixture():
+    m = _m()
+    from test_golden import named_weights
+    from mulit_view_object_detection_b200 import weights_io as wio
+    d = load("depth_sampling_add")
+    S, F = int(d["S"]), int(d["F"])
+    cfg = FusionConfig(GRID_REAS="add", samples=S, TOP_DOWN_PYRAMID_SIZE=F, NUM_VIEWS=1)
+    p = wio.fusion_params_from_keras(named_weights(d), cfg, levels=(4,))["grid_reas_depth_PG4"]
+    out = m.depth_sampling(to_dev(d["x"])[0], cfg, "grid_reas_depth_PG4", params=p)
+    close(out.cpu().numpy(), d["out"], rtol=1e-5, atol=1e-6)
