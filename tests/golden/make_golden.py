@@ -185,6 +185,47 @@ def gen_convlstm():
     save("convlstm", x=xs, W=W, b=b, h=np.stack(hs, 1), c=np.stack(cs, 1))
 
 
+def gen_convlstm_sequence():
+    """ConvRNN3D.call + get_initial_state (mrcnn/recurrent.py:143-173, 230-300) over the view axis, as convlstm() drives it
+    (model_multi.py:109-123): zero initial states shaped like the INPUT, cell applied per view, last output returned.  The
+    Keras RNN base class is replaced by a plain object carrying the attributes `call` reads; K.rnn is a Python loop."""
+    from mrcnn import recurrent as rec
+    rng = np.random.default_rng(20)
+    B, V, X, Y, Z, C = 1, 4, 3, 4, 5, 4
+    F = C
+    cell = mm.ConvLSTMCell(shape=[X, Y, Z], kernel=[3, 3, 3], filters=F)
+    W = (rng.standard_normal((3, 3, 3, C + F, 4 * F)) * 0.15).astype(np.float32)
+    b = rng.normal(0, 0.1, 4 * F).astype(np.float32)
+    cell.W, cell.bias = T(W), T(b)
+    cell.kernel_shape = [3, 3, 3, C, 4 * F]            # what ConvLSTMCell.build sets (recurrent.py:437-441)
+
+    def k_rnn(step, inputs, initial_states, constants=None, go_backwards=False, mask=None, input_length=None):
+        states, outs = list(initial_states), []
+        for t in range(arr(inputs).shape[1]):
+            out, states = step(T(arr(inputs)[:, t]), tuple(states))
+            states = list(states)
+            outs.append(arr(out))
+        return T(outs[-1]), T(np.stack(outs, 1)), states
+
+    rec.K.zeros_like = lambda x: T(np.zeros_like(arr(x)))
+    rec.K.sum = lambda x, axis=None: T(np.sum(arr(x), axis=axis, dtype=np.float32))
+    rec.K.int_shape = lambda x: tuple(int(d) for d in arr(x).shape)
+    rec.K.image_data_format = lambda: "channels_last"
+    rec.K.rnn = k_rnn
+    rec.has_arg = lambda fn, name: False
+    rec.to_list = lambda x, allow_tuple=False: list(x)
+
+    class Stub:
+        pass
+    layer = Stub()
+    layer.cell, layer.stateful, layer.states = cell, False, [None, None]
+    layer.go_backwards, layer._num_constants, layer.return_sequences, layer.return_state = False, None, False, False
+    layer.get_initial_state = lambda inputs: rec.ConvRNN3D.get_initial_state(layer, inputs)
+    xs = rng.standard_normal((B, V, X, Y, Z, C)).astype(np.float32)
+    out = quiet(rec.ConvRNN3D.call, layer, T(xs))
+    save("convlstm_sequence", x=xs, W=W, b=b, out=arr(out))
+
+
 def gen_poses():
     """mrcnn/utils.py:1175-1218 quat2rot / vec2rot -- pure NumPy, run unmodified."""
     rng = np.random.default_rng(17)
@@ -358,4 +399,5 @@ if __name__ == "__main__":
     gen_roi_align()
     gen_proposals()
     gen_convlstm()
+    gen_convlstm_sequence()
     gen_poses()

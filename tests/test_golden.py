@@ -175,3 +175,12 @@ def test_depth_sampling_wiring_and_layer_names(mode):
         out = oracle.depth_sampling(d["x"], p["weight"], p["bias"], p.get("bn"))
     assert out.shape == d["out"].shape
     np.testing.assert_allclose(out, d["out"], rtol=2e-6, atol=2e-7)
+
+
+def test_convlstm_over_views_matches_reference_convrnn3d():
+    """ConvRNN3D.call + get_initial_state executed from the reference (recurrent.py:143-173,230-300): zero initial states with the
+    input's channel count, the cell applied per view, the LAST output returned -- what convlstm() (model_multi.py:109-123) builds."""
+    d = load("convlstm_sequence")
+    out = oracle.convlstm(d["x"], d["W"], d["b"])
+    assert out.shape == d["out"].shape
+    np.testing.assert_allclose(out, d["out"], rtol=2e-6, atol=2e-7)

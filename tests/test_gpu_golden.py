@@ -120,3 +120,12 @@ def test_depth_sampling_vs_reference_fixture():
     p = wio.fusion_params_from_keras(named_weights(d), cfg, levels=(4,))["grid_reas_depth_PG4"]
     out = m.depth_sampling(to_dev(d["x"])[0], cfg, "grid_reas_depth_PG4", params=p)
     close(out.cpu().numpy(), d["out"], rtol=1e-5, atol=1e-6)
+
+
+def test_convlstm_sequence_vs_reference_convrnn3d():
+    """convlstm() over the view axis (zero initial state, last output) against the reference's ConvRNN3D.call fixture."""
+    m = _m()
+    d = load("convlstm_sequence")
+    dW, db = to_dev(d["W"], d["b"])
+    out = m.convlstm(to_dev(d["x"])[0], "golden_convlstm", kernel=(3, 3, 3), filters=d["x"].shape[-1], params={"W": dW, "b": db})
+    close(out.cpu().numpy(), d["out"], rtol=1e-5, atol=2e-6)
