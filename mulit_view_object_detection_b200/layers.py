@@ -27,7 +27,6 @@ use the Keras initial values (BatchNorm gamma=1, beta=0, mean=0, var=1).
 import ctypes as C
 
 import numpy as np
-import os
 import torch
 
 from . import _lib

@@ -1,6 +1,6 @@
 """Time one ConvLSTM step (K2) at workload c3 size: C = F = 256, 64^3 voxels: tensor-core path vs the fp32 CUDA-core kernel."""
-import sys, time
-import numpy as np, torch
+import sys
+import torch
 sys.path.insert(0, '.')
 import mulit_view_object_detection_b200 as m
 
