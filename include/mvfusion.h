@@ -65,6 +65,7 @@ typedef struct MvfGrid {
 /* flags */
 #define MVF_FLAG_RELU_IN    1  /* ReLU on each per-view sample before the reduction (:448,:459) */
 #define MVF_FLAG_RELU_OUT   2  /* ReLU after the (optional) BatchNorm affine (:404)             */
+#define MVF_FLAG_PRESPLIT   8  /* mvf_conv3d_tc: `ws` already holds the operand halves (mvf_unproject_split_f16)   */
 #define MVF_FLAG_WORLD_GRID 4  /* notebook variant: world-axis-aligned grid centred at
                                   [R0|t0].(0,0,grid_dist,1) (Notebook/projection.py:47-151,253-339) */
 
@@ -87,6 +88,15 @@ int mvf_unproject_fuse(const float* feats, const float* Rcam, const float* Rmain
                        const float* bn_scale, const float* bn_shift,
                        float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
                        void* stream);
+
+/* unproj_feat written straight into the operand format of the 'conv3d' U-Net's first convolution (model_multi.py:411-421):
+ * fp16 (hi, lo) halves in the parity-sub-lattice layout, into the workspace a following
+ * mvf_conv3d_tc(MVF_CONV_S2, flags | MVF_FLAG_PRESPLIT, in = NULL, same ws) consumes -- the fp32 per-view grids and the split
+ * pass over them never exist.  act_amax: DEVICE pointer to a bound on max|value| (max|feats| is one).  conv_ws: at least
+ * mvf_conv3d_tc_workspace_bytes(MVF_CONV_S2, 3, B, V, X, Y, Z, C, 0, Cout) bytes.  Needs C % 64 == 0 and even grid dims. */
+int mvf_unproject_split_f16(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat,
+                            const MvfGrid* g, int B, int V, int fh, int fw, int C, int img_h, int img_w,
+                            int flags, const float* act_amax, void* conv_ws, size_t ws_bytes, void* stream);
 
 /* ---- grid_reas on a materialised [B,V,N,C] tensor -------------------------------------------
  * replaces grid_reas(x, scope, config) 'add' (model_multi.py:401-404) and the oracle-defined

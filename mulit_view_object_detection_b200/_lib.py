@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmvfusion.so")
 MVF_OK = 0
 MVF_EINVAL, MVF_ENULL, MVF_EALIGN, MVF_ECUDA, MVF_EUNSUPPORTED, MVF_EWORKSPACE = -1, -2, -3, -4, -5, -6
 FUSE_NONE, FUSE_SUM, FUSE_MEAN, FUSE_MAX = 0, 1, 2, 3
-FLAG_RELU_IN, FLAG_RELU_OUT, FLAG_WORLD_GRID = 1, 2, 4
+FLAG_RELU_IN, FLAG_RELU_OUT, FLAG_WORLD_GRID, FLAG_PRESPLIT = 1, 2, 4, 8
 CONV_S1, CONV_S2, DECONV_S2 = 0, 1, 2
 MAX_VIEWS, MAX_DIM, MAX_SAMPLES, MAX_NMS_BOXES, MAX_CLASSES = 32, 192, 64, 8192, 256
 
@@ -47,6 +47,7 @@ _G = C.POINTER(MvfGrid)
 _SIGS = {
     "mvf_unproject_fuse": (_i, [_p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i,
                                 _p, _p, _p, _p, _p, _p, _p]),
+    "mvf_unproject_split_f16": (_i, [_p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "mvf_view_reduce": (_i, [_p, _i, _i, _ll, _i, _i, _i, _p, _p, _p, _p]),
     "mvf_channel_mean": (_i, [_p, _i, _i, _ll, _i, _p, _p]),
     "mvf_ident_fuse": (_i, [_p, _p, _p, _p, _p, _i, _i, _ll, _i, _i, _p, _p]),

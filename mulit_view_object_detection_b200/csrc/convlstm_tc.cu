@@ -540,25 +540,6 @@ amax_kernel(const float4* __restrict__ in, long long n4, int relu, unsigned* __r
     for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));     // non-negative floats order like their bit patterns
 }
-__device__ __forceinline__ float pow2_scale(unsigned amax_bits, float* inv) {
-    const float amax = __uint_as_float(amax_bits);
-    int sa = 0;
-    if (amax > 0.f && amax < 3.0e38f) { int e; frexpf(amax, &e); sa = min(max(14 - e, -100), 100); }
-    *inv = ldexpf(1.0f, -sa);
-    return ldexpf(1.0f, sa);
-}
-__device__ __forceinline__ void split_half4(float4 v, float scale, uint2* hi, uint2* lo) {
-    const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
-    unsigned short h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half a1 = __float2half_rn(x[i]);
-        h[i] = __half_as_ushort(a1);
-        l[i] = __half_as_ushort(__float2half_rn(x[i] - __half2float(a1)));
-    }
-    *hi = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
-    *lo = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
-}
 // activations: same indexing as act_split_kernel (optional ReLU, optional parity sub-lattice re-layout); tail[0] = amax bits, tail[1] <- 2^-s
 __global__ void __launch_bounds__(256)
 act_split_f16_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint2* __restrict__ lo, long long n4,
@@ -847,15 +828,17 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
                              const float* bn_scale, const float* bn_shift, const float* pre_scale, const float* pre_shift,
                              int kind, int ksize, int B, int V, int X, int Y, int Z, int C, int C2, int Cout, int flags,
                              float* out, void* ws, size_t ws_bytes, const float* act_amax, void* stream) {
-    if (!in || !wsplit || !bias || !out) return MVF_ENULL;
+    const bool presplit = (flags & MVF_FLAG_PRESPLIT) != 0;      // the workspace already holds the fp16 halves of `in` (+ scale)
+    if ((!in && !presplit) || !wsplit || !bias || !out) return MVF_ENULL;
     if ((bn_scale == nullptr) != (bn_shift == nullptr) || (pre_scale == nullptr) != (pre_shift == nullptr)) return MVF_ENULL;
     if ((in2 == nullptr) != (C2 == 0)) return MVF_EINVAL;
+    if (presplit && (in2 || pre_scale || kind != MVF_CONV_S2)) return MVF_EUNSUPPORTED;
     if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || C2 < 0 || Cout <= 0) return MVF_EINVAL;
     if (kind < MVF_CONV_S1 || kind > MVF_DECONV_S2 || (ksize != 1 && ksize != 3) || (kind != MVF_CONV_S1 && ksize != 3)) return MVF_EINVAL;
     if (C % TC_K != 0 || C2 % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
     if (kind == MVF_CONV_S2 && ((X | Y | Z) & 1)) return MVF_EUNSUPPORTED;      // odd sizes pad on both sides in TF; not built
     if (pre_scale && in2) return MVF_EUNSUPPORTED;
-    if (!aligned16(in) || !aligned16(wsplit) || (ws && !aligned16(ws)) || !aligned16(out) || (in2 && !aligned16(in2)) ||
+    if ((in && !aligned16(in)) || !aligned16(wsplit) || (ws && !aligned16(ws)) || !aligned16(out) || (in2 && !aligned16(in2)) ||
         (pre_scale && (!aligned16(pre_scale) || !aligned16(pre_shift)))) return MVF_EALIGN;
     if (pre_scale && ksize != 1) return MVF_EUNSUPPORTED;                       // the affine must not touch the SAME padding
     const int relu_in = (flags & MVF_FLAG_RELU_IN) != 0, s2d = kind == MVF_CONV_S2;
@@ -865,9 +848,14 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     cudaStream_t s = (cudaStream_t)stream;
     const long long n1 = (long long)B * V * X * Y * Z * C, n2 = (long long)B * X * Y * Z * C2;
     const bool f16 = split_pass && conv3d_f16(ksize, C, C2, pre_scale != nullptr);
+    if (presplit && !f16) return MVF_EUNSUPPORTED;
     const void *xh = in, *xl = in, *hh = in2, *hl = in2;
     const float* inv_a = nullptr;
-    if (f16) {
+    if (f16 && presplit) {                               // written by mvf_unproject_split_f16
+        __half* w0 = (__half*)ws;
+        xh = w0; xl = w0 + n1; hh = xh; hl = xl;
+        inv_a = (const float*)(((uintptr_t)(w0 + 2 * n1) + 15) & ~(uintptr_t)15) + 1;
+    } else if (f16) {
         __half* w0 = (__half*)ws; __half* w1 = w0 + n1; __half* w2 = w1 + n1; __half* w3 = w2 + n2;
         unsigned* tail = (unsigned*)(((uintptr_t)(w3 + n2) + 15) & ~(uintptr_t)15);
         if (act_amax) {                                  // the caller's bound on max|operand| (e.g. max|features| for unprojected grids)

@@ -1,6 +1,7 @@
 // Shared device/host helpers for libmvfusion (sm_100a).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <math.h>
 #include <atomic>
@@ -91,6 +92,28 @@ __device__ __forceinline__ ulonglong2 fma2x2(float w, ulonglong2 t, ulonglong2 a
 }
 __device__ __forceinline__ float4 unpack4(ulonglong2 v) { const float2 a = unpack2(v.x), b = unpack2(v.y); return make_float4(a.x, a.y, b.x, b.y); }
 __device__ __forceinline__ ulonglong2 pack4(float4 v) { ulonglong2 r; r.x = pack2(v.x, v.y); r.y = pack2(v.z, v.w); return r; }
+
+// ---- fp16 operand split of the tensor-core convolutions (convlstm_tc.cu; also written directly by unproject.cu) ----
+// scale 2^s with s = 14 - exponent(amax): a*2^s = a1 + a2 in two fp16 halves; *inv = 2^-s
+__device__ __forceinline__ float pow2_scale(unsigned amax_bits, float* inv) {
+    const float amax = __uint_as_float(amax_bits);
+    int sa = 0;
+    if (amax > 0.f && amax < 3.0e38f) { int e; frexpf(amax, &e); sa = min(max(14 - e, -100), 100); }
+    *inv = ldexpf(1.0f, -sa);
+    return ldexpf(1.0f, sa);
+}
+__device__ __forceinline__ void split_half4(float4 v, float scale, uint2* hi, uint2* lo) {
+    const float x[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half a1 = __float2half_rn(x[i]);
+        h[i] = __half_as_ushort(a1);
+        l[i] = __half_as_ushort(__float2half_rn(x[i] - __half2float(a1)));
+    }
+    *hi = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+    *lo = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+}
 
 // ---- host: TF1 RangeOp<float> / LinSpaceOp<float> fill order ---------------------------------
 // (third-party kernels restated; call sites mrcnn/model_multi.py:157-160, :267)

@@ -14,6 +14,9 @@ struct UnprojParams {
     const float* feats; const float* Rcam; const float* Rmain; const float* Kmat;
     const float* bn_scale; const float* bn_shift;
     float* out; int32_t* out_idx; uint8_t* out_valid; float* out_grid_pos;
+    // mode NONE only: write the per-view grids as the fp16 (hi, lo) halves of a stride-2 conv operand (parity sub-lattice layout
+    // [B*V, 8, X/2, Y/2, Z/2, C]) instead of fp32; split_tail[0] = bits of the bound on max|value|, split_tail[1] <- 2^-s
+    uint2* out16_hi; uint2* out16_lo; unsigned* split_tail;
     int B, V, fh, fw, C, X, Y, Z, x_begin, Xs;
     int mode, flags;
     float sx, sy, inv_v, grid_dist;
@@ -133,6 +136,12 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
     const size_t view_bytes = view_stride * sizeof(float);
     const char* vbase = (const char*)feats_b + lane_off[0];
     const bool has_bn = p.bn_scale != nullptr, relu_out = (p.flags & MVF_FLAG_RELU_OUT) != 0;
+    float split_scale = 1.0f;
+    if (MODE == MVF_FUSE_NONE && p.out16_hi) {
+        float inv;
+        split_scale = pow2_scale(p.split_tail[0], &inv);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) reinterpret_cast<float*>(p.split_tail)[1] = inv;
+    }
     float* const obase0 = (MODE == MVF_FUSE_NONE) ? nullptr : p.out + (((size_t)b * p.Xs + ixs) * p.Y + iy) * p.Z * C + 4 * c4base;
 
     const ulonglong2 zz = make_ulonglong2(0ull, 0ull);
@@ -330,8 +339,17 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
                         if (RELU_IN) val = relu4(val);
                         if (MODE == MVF_FUSE_NONE) {
                             if (z0 + k < p.Z && (FULLC || c4base + 32 * c < C4)) {
-                                float* o = p.out + ((((size_t)b * V + vv) * p.Xs + ixs) * p.Y * p.Z + (size_t)iy * p.Z + z0 + k) * C;
-                                stcs4(o + 4 * (c4base + 32 * c), val);
+                                if (p.out16_hi) {                  // operand halves for the U-Net's stride-2 conv (whole grid, even dims)
+                                    const int z = z0 + k, sub = ((ixs & 1) * 2 + (iy & 1)) * 2 + (z & 1);
+                                    const size_t o = ((((((size_t)b * V + vv) * 8 + sub) * (p.X / 2) + (ixs >> 1)) * (p.Y / 2) + (iy >> 1)) * (p.Z / 2)
+                                                      + (z >> 1)) * C4 + c4base + 32 * c;
+                                    uint2 h2, l2;
+                                    split_half4(val, split_scale, &h2, &l2);
+                                    p.out16_hi[o] = h2; p.out16_lo[o] = l2;
+                                } else {
+                                    float* o = p.out + ((((size_t)b * V + vv) * p.Xs + ixs) * p.Y * p.Z + (size_t)iy * p.Z + z0 + k) * C;
+                                    stcs4(o + 4 * (c4base + 32 * c), val);
+                                }
                             }
                         } else if (MODE == MVF_FUSE_MAX) {
                             acc[k][c] = (vv == 0) ? pack4(val) : pack4(max4(unpack4(acc[k][c]), val));
@@ -433,17 +451,17 @@ int fill_centres(const MvfGrid* g, int flags, float* gx, float* gy, float* gz) {
 
 using namespace mvf;
 
-extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat,
-                                  const MvfGrid* g, int B, int V, int fh, int fw, int C, int img_h, int img_w,
-                                  int mode, int flags, double grid_dist, int x_begin, int x_count,
-                                  const float* bn_scale, const float* bn_shift,
-                                  float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
-                                  void* stream) {
-    if (!feats || !Rcam || !Kmat || !g || !out) return MVF_ENULL;
+static int unproject_impl(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat,
+                          const MvfGrid* g, int B, int V, int fh, int fw, int C, int img_h, int img_w,
+                          int mode, int flags, double grid_dist, int x_begin, int x_count,
+                          const float* bn_scale, const float* bn_shift,
+                          float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
+                          uint2* out16_hi, uint2* out16_lo, unsigned* split_tail, void* stream) {
+    if (!feats || !Rcam || !Kmat || !g || (!out && !out16_hi)) return MVF_ENULL;
     if (B <= 0 || V <= 0 || fh <= 0 || fw <= 0 || C <= 0 || img_h <= 0 || img_w <= 0) return MVF_EINVAL;
     if (mode < MVF_FUSE_NONE || mode > MVF_FUSE_MAX) return MVF_EINVAL;
     if ((bn_scale == nullptr) != (bn_shift == nullptr)) return MVF_ENULL;
-    if (C % 4 != 0 || !aligned16(feats) || !aligned16(out) || (bn_scale && (!aligned16(bn_scale) || !aligned16(bn_shift))))
+    if (C % 4 != 0 || !aligned16(feats) || (out && !aligned16(out)) || (bn_scale && (!aligned16(bn_scale) || !aligned16(bn_shift))))
         return MVF_EALIGN;
     if (V > MVF_MAX_VIEWS || C > 1024 || B > 65535) return MVF_EUNSUPPORTED;
     if ((size_t)fh * fw * C >= (size_t)1 << 30) return MVF_EUNSUPPORTED;   // byte offsets inside a view fit 32 bits
@@ -456,6 +474,7 @@ extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const f
     p.bn_scale = (mode == MVF_FUSE_NONE) ? nullptr : bn_scale;
     p.bn_shift = (mode == MVF_FUSE_NONE) ? nullptr : bn_shift;
     p.out = out; p.out_idx = out_idx; p.out_valid = out_valid; p.out_grid_pos = out_grid_pos;
+    p.out16_hi = out16_hi; p.out16_lo = out16_lo; p.split_tail = split_tail;
     p.B = B; p.V = V; p.fh = fh; p.fw = fw; p.C = C;
     p.X = g->nvox; p.Y = g->nvox; p.Z = g->nvox_z; p.x_begin = x_begin; p.Xs = x_count;
     p.mode = mode; p.flags = (mode == MVF_FUSE_NONE) ? (flags & ~MVF_FLAG_RELU_OUT) : flags;
@@ -473,4 +492,35 @@ extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const f
     if (variant == 2) return launch_run<2, 8>(p, B, s);
     if (variant == 3) return launch_run<1, 8>(p, B, s);
     return (C4 % 64 == 0) ? launch_run<2, 8>(p, B, s) : launch_run<1, 16>(p, B, s);
+}
+
+extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat,
+                                  const MvfGrid* g, int B, int V, int fh, int fw, int C, int img_h, int img_w,
+                                  int mode, int flags, double grid_dist, int x_begin, int x_count,
+                                  const float* bn_scale, const float* bn_shift,
+                                  float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
+                                  void* stream) {
+    if (!out) return MVF_ENULL;
+    return unproject_impl(feats, Rcam, Rmain, Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, grid_dist, x_begin, x_count,
+                          bn_scale, bn_shift, out, out_idx, out_valid, out_grid_pos, nullptr, nullptr, nullptr, stream);
+}
+
+// unproj_feat straight into the operand format of the U-Net's first convolution (model_multi.py:411-421): the per-view grids
+// are written once, as fp16 (hi, lo) halves in the parity-sub-lattice layout mvf_conv3d_tc(MVF_CONV_S2, MVF_FLAG_PRESPLIT)
+// reads, instead of fp32 grids that a split pass would re-read and re-write (4.3 GB at 64^3 with 8 views).
+// act_amax: DEVICE pointer to a bound on max|value| -- max|feats| is one (bilinear weights are in [0,1] and sum to <= 1).
+extern "C" int mvf_unproject_split_f16(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat,
+                                       const MvfGrid* g, int B, int V, int fh, int fw, int C, int img_h, int img_w,
+                                       int flags, const float* act_amax, void* conv_ws, size_t ws_bytes, void* stream) {
+    if (!g || !act_amax || !conv_ws) return MVF_ENULL;
+    if (B <= 0 || V <= 0 || C <= 0) return MVF_EINVAL;
+    if (C % 64 != 0 || (g->nvox & 1) || (g->nvox_z & 1) || (flags & MVF_FLAG_WORLD_GRID)) return MVF_EUNSUPPORTED;
+    if (!aligned16(conv_ws)) return MVF_EALIGN;
+    const size_t n1 = (size_t)B * V * g->nvox * g->nvox * g->nvox_z * C;             // elements of the per-view grids
+    if (ws_bytes < 4 * n1 + 256) return MVF_EWORKSPACE;                                // [hi n1 halves][lo n1 halves][tail]
+    __half* w0 = (__half*)conv_ws;
+    unsigned* tail = (unsigned*)(((uintptr_t)(w0 + 2 * n1) + 15) & ~(uintptr_t)15);
+    if (cudaMemcpyAsync(tail, act_amax, 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) return MVF_ECUDA;
+    return unproject_impl(feats, Rcam, Rmain, Kmat, g, B, V, fh, fw, C, img_h, img_w, MVF_FUSE_NONE, flags & MVF_FLAG_RELU_IN, 0.0, 0, 0,
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (uint2*)w0, (uint2*)(w0 + n1), tail, stream);
 }

@@ -375,6 +375,25 @@ class Conv3dTensorCore:
             return 2 * X, 2 * Y, 2 * Z
         return X, Y, Z
 
+    def workspace(self, B, X, Y, Z, device):
+        """The device scratch of a call on a [B,V,X,Y,Z,C] input (None when the library splits inside the GEMM)."""
+        need = lib.mvf_conv3d_tc_workspace_bytes(self.kind, self.ksize, B, self.V, X, Y, Z, self.C, self.C2, self.Cout)
+        if need and (self._ws is None or self._ws.numel() * 4 < need or self._ws.device != device):
+            self._ws = torch.empty(need // 4, dtype=torch.float32, device=device)
+        return self._ws if need else None
+
+    def call_presplit(self, B, X, Y, Z, relu_out=True):
+        """Run on operand halves already written into ``self.workspace(...)`` by ``mvf_unproject_split_f16``."""
+        ws = self.workspace(B, X, Y, Z, self.bias.device)
+        OX, OY, OZ = self.out_dims(X, Y, Z)
+        out = torch.empty((B, OX, OY, OZ, self.Cout), dtype=torch.float32, device=self.bias.device)
+        flags = _lib.FLAG_PRESPLIT | (_lib.FLAG_RELU_OUT if relu_out else 0)
+        rc = lib.mvf_conv3d_tc(None, None, _ptr(self.wsplit), _ptr(self.bias), _ptr(self.scale), _ptr(self.shift), None, None,
+                               self.kind, self.ksize, B, self.V, X, Y, Z, self.C, self.C2, self.Cout, flags,
+                               _ptr(out), _ptr(ws), ws.numel() * 4, None, _stream())
+        check(rc, "mvf_conv3d_tc")
+        return out
+
     def __call__(self, x, x2=None, relu_in=False, relu_out=True, pre=None, act_amax=None):
         """x [B,V,X,Y,Z,C] (or [B,X,Y,Z,C] when V == 1); x2 [B,X,Y,Z,C2] appended on channels; ``pre`` = (scale, shift)
         per input channel [V*C] applied before the conv (a depthwise 1x1); ``act_amax``: 1-element device tensor bounding
@@ -420,15 +439,19 @@ def _cached_conv(name, p, kind, **kw):
     return hit[1]
 
 
-def unet_fuse(x, scope, config, params, act_amax=None):
+def unet_fuse(x, scope, config, params, act_amax=None, conv1_out=None):
     """``GRID_REAS='conv3d'`` (model_multi.py:406-441): the MLF U-Net over the view-concatenated grids, four tensor-core
-    convolutions; the per-view grids [B,V,X,Y,Z,C] are consumed in place (no transpose / reshape / concat copies)."""
-    x = _cuda(x, "inputs")
-    B, V, X, Y, Z, Cc = x.shape
-    if X % 4 or Y % 4 or Z % 4:
-        raise ValueError("the conv3d U-Net halves the grid twice: nvox and nvox_z must be multiples of 4")
+    convolutions; the per-view grids [B,V,X,Y,Z,C] are consumed in place (no transpose / reshape / concat copies).
+    ``conv1_out``: the first convolution's output when the caller already produced it (``unproject_unet_fuse``)."""
     name = scope + "_3D_conv"
-    conv1 = _cached_conv(name + "_1", params["conv1"], "conv_s2", V=V)(x, relu_in=True, act_amax=act_amax)   # :415-421
+    if conv1_out is None:
+        x = _cuda(x, "inputs")
+        B, V, X, Y, Z, Cc = x.shape
+        if X % 4 or Y % 4 or Z % 4:
+            raise ValueError("the conv3d U-Net halves the grid twice: nvox and nvox_z must be multiples of 4")
+        conv1 = _cached_conv(name + "_1", params["conv1"], "conv_s2", V=V)(x, relu_in=True, act_amax=act_amax)   # :415-421
+    else:
+        conv1 = conv1_out
     conv2 = _cached_conv(name + "_2", params["conv2"], "conv_s2")(conv1)                                # :423-428
     deconv1 = _cached_conv(name + "_deconv_1", params["deconv1"], "deconv_s2")(conv2)                   # :430-436
     C2 = conv1.shape[-1]
@@ -638,6 +661,34 @@ def unproject_fuse_project(feats, Rcam, Kmat, config, proj_size, mode="sum", bn=
     return rays, fused
 
 
+def unproject_unet_fuse(feats, Rcam, Kmat, scope, config, params):
+    """``grid_reas(unproj_feat(...))`` for GRID_REAS='conv3d' (model_multi.py:2382-2392 with :406-441) without materialising the
+    per-view grids: K1 writes them once, as the fp16 operand halves of the U-Net's first convolution
+    (``mvf_unproject_split_f16``; the fp32 grids and the 4.3 GB split pass over them never exist at 64^3 x 8 views), scaled by
+    a power of two taken from max|features| (a bound: bilinear weights are in [0,1] and sum to at most 1).
+    Needs C % 64 == 0 and grid dims divisible by 4; returns None when the shapes do not qualify (caller falls back)."""
+    feats, Rcam, Kmat = _cuda(feats, "feats"), _cuda(Rcam, "Rcam"), _cuda(Kmat, "Kmat")
+    B, V, fh, fw, Cc = feats.shape
+    g = grid_from_config(config)
+    X, Z = g.nvox, g.nvox_z
+    if Cc % 64 or X % 4 or Z % 4:
+        return None
+    conv1 = _cached_conv(scope + "_3D_conv_1", params["conv1"], "conv_s2", V=V)
+    ws = conv1.workspace(B, X, X, Z, feats.device)
+    bound = feats.abs().amax().reshape(1)
+    ih, iw = _image_hw(config)
+    rc = lib.mvf_unproject_split_f16(_ptr(feats), _ptr(Rcam), None, _ptr(Kmat), C.byref(g), B, V, fh, fw, Cc, ih, iw,
+                                     _lib.FLAG_RELU_IN, _ptr(bound), _ptr(ws), ws.numel() * 4, _stream())
+    if rc == _lib.MVF_EUNSUPPORTED:
+        return None
+    check(rc, "mvf_unproject_split_f16")
+    try:
+        c1 = conv1.call_presplit(B, X, X, Z)
+    except ValueError:                                  # the library chose the tf32 format for these channel counts
+        return None
+    return unet_fuse(None, scope, config, params, conv1_out=c1)
+
+
 def fusion_neck(feature_maps, Rcam, Kmat, config, params=None, levels=(2, 3, 4, 5, 6), proj_sizes=None):
     """The fusion neck of ``MaskRCNN.build`` (model_multi.py:2382-2410): per pyramid level
     ``unproj_feat -> grid_reas -> proj_grid -> depth_sampling``, the caller of every kernel of the path.
@@ -665,12 +716,14 @@ def fusion_neck(feature_maps, Rcam, Kmat, config, params=None, levels=(2, 3, 4, 
             fused = unproject_fuse(fm, Rcam, Kmat, config, mode="sum", bn=gp.get("bn", _default_bn(Cc)), relu_out=True)
             outs.append(proj_grid_depth_sampling([fused, Rcam, Kmat], config, P_, dname, params=dp))
             continue
-        per_view = unproj_feat([fm, Rcam, Kmat], config)
-        # bilinear weights are in [0,1] and sum to at most 1, so the unprojected grids are bounded by max|features|: the U-Net's
-        # first conv takes its fp16 operand scale from this (tiny) reduction instead of a pass over the 2 GB of grids
-        bound = fm.abs().amax().reshape(1) if config.GRID_REAS == "conv3d" else None
-        fused = grid_reas(per_view, gname, config, params=gp, act_amax=bound)
-        del per_view
+        fused = unproject_unet_fuse(fm, Rcam, Kmat, gname, config, gp) if config.GRID_REAS == "conv3d" else None
+        if fused is None:
+            per_view = unproj_feat([fm, Rcam, Kmat], config)
+            # bilinear weights are in [0,1] and sum to at most 1, so the unprojected grids are bounded by max|features|: the
+            # U-Net's first conv takes its fp16 operand scale from this (tiny) reduction instead of a pass over the grids
+            bound = fm.abs().amax().reshape(1) if config.GRID_REAS == "conv3d" else None
+            fused = grid_reas(per_view, gname, config, params=gp, act_amax=bound)
+            del per_view
         rays = proj_grid([fused, Rcam, Kmat], config, P_)
         outs.append(depth_sampling(rays, config, dname, params=dp))
     return outs

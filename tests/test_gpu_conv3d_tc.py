@@ -166,8 +166,18 @@ def test_fusion_neck_conv3d_mode():
             "conv1": _layer(rng, (F * S, 64), F * S, 64),
             "dw2": {"w": rng.uniform(0.5, 1.5, 64).astype(np.float32), "b": rng.normal(0, 0.1, 64).astype(np.float32)},
             "conv2": _layer(rng, (64, F), 64, F)}
-    outs = m.fusion_neck(to_dev(*fmaps), *to_dev(Rcam, Kmat), cfg, params=m.prepare_params(params), levels=levels)
+    prepared = m.prepare_params(params)
+    dfm, (dR, dK) = to_dev(*fmaps), to_dev(Rcam, Kmat)
+    outs = m.fusion_neck(dfm, dR, dK, cfg, params=prepared, levels=levels)
     refs = oracle.fusion_neck(fmaps, Rcam, Kmat, cfg, params, levels=levels)
     for o, r in zip(outs, refs):
         assert tuple(o.shape) == r.shape
         close(o.cpu().numpy(), r, rtol=1e-5, atol=5e-6)
+    # the neck took the direct path (K1 writes the operand halves of the first conv); it must equal the materialised path
+    # (fp32 per-view grids + split pass with the same scale bound) bit for bit
+    import torch
+    direct = m.unproject_unet_fuse(dfm[0], dR, dK, "grid_reas_P4", cfg, prepared["grid_reas_P4"])
+    assert direct is not None
+    bound = dfm[0].abs().amax().reshape(1)
+    mat = m.grid_reas(m.unproj_feat([dfm[0], dR, dK], cfg), "grid_reas_P4", cfg, params=prepared["grid_reas_P4"], act_amax=bound)
+    assert torch.equal(direct, mat)
