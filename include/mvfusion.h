@@ -89,14 +89,16 @@ int mvf_unproject_fuse(const float* feats, const float* Rcam, const float* Rmain
                        float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
                        void* stream);
 
-/* unproj_feat written straight into the operand format of the 'conv3d' U-Net's first convolution (model_multi.py:411-421):
- * fp16 (hi, lo) halves in the parity-sub-lattice layout, into the workspace a following
- * mvf_conv3d_tc(MVF_CONV_S2, flags | MVF_FLAG_PRESPLIT, in = NULL, same ws) consumes -- the fp32 per-view grids and the split
- * pass over them never exist.  act_amax: DEVICE pointer to a bound on max|value| (max|feats| is one).  conv_ws: at least
- * mvf_conv3d_tc_workspace_bytes(MVF_CONV_S2, 3, B, V, X, Y, Z, C, 0, Cout) bytes.  Needs C % 64 == 0 and even grid dims. */
+/* unproj_feat written straight into the operand format of the convolution that consumes it -- the 'conv3d' U-Net's first
+ * convolution (model_multi.py:411-421; sublattices = 1: parity-sub-lattice layout of MVF_CONV_S2) or the 'ident' 1x1x1 conv
+ * (:446-453; sublattices = 0) -- as fp16 (hi, lo) halves, into the workspace a following
+ * mvf_conv3d_tc(flags | MVF_FLAG_PRESPLIT, in = NULL, same ws) reads: the fp32 per-view grids and the split pass over them never
+ * exist.  The weights of that convolution are prepared with chan_interleave = -1 (fp16 format whatever the kernel size).
+ * act_amax: DEVICE pointer to a bound on max|value| (max|feats| is one).  conv_ws: 4 * B*V*X*Y*Z*C + 256 bytes at least.
+ * Needs C % 64 == 0 (and even grid dims with sublattices). */
 int mvf_unproject_split_f16(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat,
                             const MvfGrid* g, int B, int V, int fh, int fw, int C, int img_h, int img_w,
-                            int flags, const float* act_amax, void* conv_ws, size_t ws_bytes, void* stream);
+                            int flags, int sublattices, const float* act_amax, void* conv_ws, size_t ws_bytes, void* stream);
 
 /* ---- grid_reas on a materialised [B,V,N,C] tensor -------------------------------------------
  * replaces grid_reas(x, scope, config) 'add' (model_multi.py:401-404) and the oracle-defined

@@ -8,7 +8,7 @@ built -- there is no CPU or pure-PyTorch fallback.
 from .config import FusionConfig
 from . import _lib
 from ._lib import LIB_PATH, launch_count, version
-from .layers import (unproj_feat, unproj_feat_notebook, grid_reas, convlstm, convlstm_step, ConvLSTMTensorCore, Conv3dTensorCore, unet_fuse, unproject_unet_fuse,
+from .layers import (unproj_feat, unproj_feat_notebook, grid_reas, convlstm, convlstm_step, ConvLSTMTensorCore, Conv3dTensorCore, unet_fuse, unproject_unet_fuse, unproject_ident_fuse,
                      proj_grid, depth_sampling, depth_sampling_conv3d, proj_grid_depth_sampling, PyramidROIAlign, refine_detections_graph,
                      DetectionLayer, ProposalLayer, non_max_suppression, unproject_fuse,
                      unproject_fuse_project, fusion_neck, prepare_params, view_reduce, channel_mean, HostPipeline, set_weights, weights, reused_lay)
@@ -16,7 +16,7 @@ from .layers import (unproj_feat, unproj_feat_notebook, grid_reas, convlstm, con
 __all__ = [
     "FusionConfig", "LIB_PATH", "launch_count", "version",
     "unproj_feat", "unproj_feat_notebook", "grid_reas", "convlstm", "convlstm_step", "ConvLSTMTensorCore", "Conv3dTensorCore",
-    "unet_fuse", "unproject_unet_fuse", "proj_grid", "depth_sampling", "depth_sampling_conv3d", "proj_grid_depth_sampling", "PyramidROIAlign", "refine_detections_graph",
+    "unet_fuse", "unproject_unet_fuse", "unproject_ident_fuse", "proj_grid", "depth_sampling", "depth_sampling_conv3d", "proj_grid_depth_sampling", "PyramidROIAlign", "refine_detections_graph",
     "DetectionLayer", "ProposalLayer", "non_max_suppression", "unproject_fuse",
     "unproject_fuse_project", "fusion_neck", "prepare_params", "view_reduce", "channel_mean", "HostPipeline", "set_weights", "weights", "reused_lay",
 ]

@@ -47,7 +47,7 @@ _G = C.POINTER(MvfGrid)
 _SIGS = {
     "mvf_unproject_fuse": (_i, [_p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i,
                                 _p, _p, _p, _p, _p, _p, _p]),
-    "mvf_unproject_split_f16": (_i, [_p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "mvf_unproject_split_f16": (_i, [_p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "mvf_view_reduce": (_i, [_p, _i, _i, _ll, _i, _i, _i, _p, _p, _p, _p]),
     "mvf_channel_mean": (_i, [_p, _i, _i, _ll, _i, _p, _p]),
     "mvf_ident_fuse": (_i, [_p, _p, _p, _p, _p, _i, _i, _ll, _i, _i, _p, _p]),

@@ -775,11 +775,15 @@ extern "C" size_t mvf_conv3d_wsplit_bytes(int kind, int ksize, int Cin, int Cout
 }
 
 static bool conv3d_f16(int ksize, int C, int C2, bool pre_affine) { return ksize == 3 && !pre_affine && want_f16(C, C2); }
+static bool conv3d_f16_presplit(int C, int C2) { return C % TC_K16 == 0 && C2 % TC_K16 == 0 && !env_flag("MVF_TC_TF32"); }
 
 extern "C" int mvf_conv3d_prepare(const float* W, int kind, int ksize, int V, int C, int C2, int Cout, int chan_interleave,
                                   float* wsplit, void* stream) {
     if (!W || !wsplit) return MVF_ENULL;
+    const bool for_presplit = chan_interleave == -1;      // weights for mvf_conv3d_tc(MVF_FLAG_PRESPLIT): always the fp16 format
+    if (for_presplit) chan_interleave = 0;
     if (V <= 0 || C <= 0 || C2 < 0 || Cout <= 0 || chan_interleave < 0) return MVF_EINVAL;
+    if (for_presplit && !conv3d_f16_presplit(C, C2)) return MVF_EUNSUPPORTED;
     if (kind < MVF_CONV_S1 || kind > MVF_DECONV_S2 || (ksize != 1 && ksize != 3) || (kind != MVF_CONV_S1 && ksize != 3)) return MVF_EINVAL;
     if (C % TC_K != 0 || C2 % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
     const int Cin = V * C + C2;
@@ -787,7 +791,7 @@ extern "C" int mvf_conv3d_prepare(const float* W, int kind, int ksize, int V, in
     const int K = conv_taps(kind, ksize) * Cin;
     const long long total = (long long)K * Cout;
     cudaStream_t s = (cudaStream_t)stream;
-    if (conv3d_f16(ksize, C, C2, false)) {       // [hi K*Cout halves][lo][amax bits, 2^-s]
+    if (for_presplit || conv3d_f16(ksize, C, C2, false)) {       // [hi K*Cout halves][lo][amax bits, 2^-s]
         __half* whi = (__half*)wsplit;
         unsigned* tail = (unsigned*)(whi + 2 * total);
         if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
@@ -832,7 +836,7 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     if ((!in && !presplit) || !wsplit || !bias || !out) return MVF_ENULL;
     if ((bn_scale == nullptr) != (bn_shift == nullptr) || (pre_scale == nullptr) != (pre_shift == nullptr)) return MVF_ENULL;
     if ((in2 == nullptr) != (C2 == 0)) return MVF_EINVAL;
-    if (presplit && (in2 || pre_scale || kind != MVF_CONV_S2)) return MVF_EUNSUPPORTED;
+    if (presplit && (in2 || pre_scale || kind == MVF_DECONV_S2)) return MVF_EUNSUPPORTED;
     if (B <= 0 || V <= 0 || X <= 0 || Y <= 0 || Z <= 0 || C <= 0 || C2 < 0 || Cout <= 0) return MVF_EINVAL;
     if (kind < MVF_CONV_S1 || kind > MVF_DECONV_S2 || (ksize != 1 && ksize != 3) || (kind != MVF_CONV_S1 && ksize != 3)) return MVF_EINVAL;
     if (C % TC_K != 0 || C2 % TC_K != 0 || Cout % 16 != 0) return MVF_EUNSUPPORTED;
@@ -842,13 +846,13 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
         (pre_scale && (!aligned16(pre_scale) || !aligned16(pre_shift)))) return MVF_EALIGN;
     if (pre_scale && ksize != 1) return MVF_EUNSUPPORTED;                       // the affine must not touch the SAME padding
     const int relu_in = (flags & MVF_FLAG_RELU_IN) != 0, s2d = kind == MVF_CONV_S2;
-    const bool split_pass = !conv3d_fused_split(kind, ksize, B, X, Y, Z, Cout);
-    if (split_pass && (!ws || ws_bytes < mvf_conv3d_tc_workspace_bytes(kind, ksize, B, V, X, Y, Z, C, C2, Cout))) return MVF_EWORKSPACE;
+    const bool split_pass = presplit || !conv3d_fused_split(kind, ksize, B, X, Y, Z, Cout);
+    if (split_pass && !presplit && (!ws || ws_bytes < mvf_conv3d_tc_workspace_bytes(kind, ksize, B, V, X, Y, Z, C, C2, Cout))) return MVF_EWORKSPACE;
     if (!encode_tiled()) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
     const long long n1 = (long long)B * V * X * Y * Z * C, n2 = (long long)B * X * Y * Z * C2;
-    const bool f16 = split_pass && conv3d_f16(ksize, C, C2, pre_scale != nullptr);
-    if (presplit && !f16) return MVF_EUNSUPPORTED;
+    const bool f16 = presplit ? conv3d_f16_presplit(C, C2) : (split_pass && conv3d_f16(ksize, C, C2, pre_scale != nullptr));
+    if (presplit && (!f16 || !ws || ws_bytes < 4 * (size_t)n1 + 256)) return presplit && !f16 ? MVF_EUNSUPPORTED : MVF_EWORKSPACE;
     const void *xh = in, *xl = in, *hh = in2, *hl = in2;
     const float* inv_a = nullptr;
     if (f16 && presplit) {                               // written by mvf_unproject_split_f16

@@ -16,7 +16,7 @@ struct UnprojParams {
     float* out; int32_t* out_idx; uint8_t* out_valid; float* out_grid_pos;
     // mode NONE only: write the per-view grids as the fp16 (hi, lo) halves of a stride-2 conv operand (parity sub-lattice layout
     // [B*V, 8, X/2, Y/2, Z/2, C]) instead of fp32; split_tail[0] = bits of the bound on max|value|, split_tail[1] <- 2^-s
-    uint2* out16_hi; uint2* out16_lo; unsigned* split_tail;
+    uint2* out16_hi; uint2* out16_lo; unsigned* split_tail; int out16_s2d;
     int B, V, fh, fw, C, X, Y, Z, x_begin, Xs;
     int mode, flags;
     float sx, sy, inv_v, grid_dist;
@@ -341,8 +341,10 @@ unproject_slot_kernel(const __grid_constant__ UnprojParams p, int nchunk, int zs
                             if (z0 + k < p.Z && (FULLC || c4base + 32 * c < C4)) {
                                 if (p.out16_hi) {                  // operand halves for the U-Net's stride-2 conv (whole grid, even dims)
                                     const int z = z0 + k, sub = ((ixs & 1) * 2 + (iy & 1)) * 2 + (z & 1);
-                                    const size_t o = ((((((size_t)b * V + vv) * 8 + sub) * (p.X / 2) + (ixs >> 1)) * (p.Y / 2) + (iy >> 1)) * (p.Z / 2)
-                                                      + (z >> 1)) * C4 + c4base + 32 * c;
+                                    const size_t o = p.out16_s2d
+                                        ? ((((((size_t)b * V + vv) * 8 + sub) * (p.X / 2) + (ixs >> 1)) * (p.Y / 2) + (iy >> 1)) * (p.Z / 2)
+                                           + (z >> 1)) * C4 + c4base + 32 * c
+                                        : (((((size_t)b * V + vv) * p.X + ixs) * p.Y + iy) * p.Z + z) * C4 + c4base + 32 * c;
                                     uint2 h2, l2;
                                     split_half4(val, split_scale, &h2, &l2);
                                     p.out16_hi[o] = h2; p.out16_lo[o] = l2;
@@ -456,7 +458,7 @@ static int unproject_impl(const float* feats, const float* Rcam, const float* Rm
                           int mode, int flags, double grid_dist, int x_begin, int x_count,
                           const float* bn_scale, const float* bn_shift,
                           float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
-                          uint2* out16_hi, uint2* out16_lo, unsigned* split_tail, void* stream) {
+                          uint2* out16_hi, uint2* out16_lo, unsigned* split_tail, int out16_s2d, void* stream) {
     if (!feats || !Rcam || !Kmat || !g || (!out && !out16_hi)) return MVF_ENULL;
     if (B <= 0 || V <= 0 || fh <= 0 || fw <= 0 || C <= 0 || img_h <= 0 || img_w <= 0) return MVF_EINVAL;
     if (mode < MVF_FUSE_NONE || mode > MVF_FUSE_MAX) return MVF_EINVAL;
@@ -474,7 +476,7 @@ static int unproject_impl(const float* feats, const float* Rcam, const float* Rm
     p.bn_scale = (mode == MVF_FUSE_NONE) ? nullptr : bn_scale;
     p.bn_shift = (mode == MVF_FUSE_NONE) ? nullptr : bn_shift;
     p.out = out; p.out_idx = out_idx; p.out_valid = out_valid; p.out_grid_pos = out_grid_pos;
-    p.out16_hi = out16_hi; p.out16_lo = out16_lo; p.split_tail = split_tail;
+    p.out16_hi = out16_hi; p.out16_lo = out16_lo; p.split_tail = split_tail; p.out16_s2d = out16_s2d;
     p.B = B; p.V = V; p.fh = fh; p.fw = fw; p.C = C;
     p.X = g->nvox; p.Y = g->nvox; p.Z = g->nvox_z; p.x_begin = x_begin; p.Xs = x_count;
     p.mode = mode; p.flags = (mode == MVF_FUSE_NONE) ? (flags & ~MVF_FLAG_RELU_OUT) : flags;
@@ -502,19 +504,20 @@ extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const f
                                   void* stream) {
     if (!out) return MVF_ENULL;
     return unproject_impl(feats, Rcam, Rmain, Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, grid_dist, x_begin, x_count,
-                          bn_scale, bn_shift, out, out_idx, out_valid, out_grid_pos, nullptr, nullptr, nullptr, stream);
+                          bn_scale, bn_shift, out, out_idx, out_valid, out_grid_pos, nullptr, nullptr, nullptr, 0, stream);
 }
 
-// unproj_feat straight into the operand format of the U-Net's first convolution (model_multi.py:411-421): the per-view grids
-// are written once, as fp16 (hi, lo) halves in the parity-sub-lattice layout mvf_conv3d_tc(MVF_CONV_S2, MVF_FLAG_PRESPLIT)
-// reads, instead of fp32 grids that a split pass would re-read and re-write (4.3 GB at 64^3 with 8 views).
+// unproj_feat straight into the operand format of the convolution that follows it (the U-Net's first conv, model_multi.py:411-421:
+// sublattices = 1, the parity-sub-lattice layout of MVF_CONV_S2; 'ident', :446-453: sublattices = 0, plain layout): the per-view
+// grids are written once, as the fp16 (hi, lo) halves mvf_conv3d_tc(MVF_FLAG_PRESPLIT) reads, instead of fp32 grids that a split pass would re-read and re-write (4.3 GB at 64^3 with 8 views).
 // act_amax: DEVICE pointer to a bound on max|value| -- max|feats| is one (bilinear weights are in [0,1] and sum to <= 1).
 extern "C" int mvf_unproject_split_f16(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat,
                                        const MvfGrid* g, int B, int V, int fh, int fw, int C, int img_h, int img_w,
-                                       int flags, const float* act_amax, void* conv_ws, size_t ws_bytes, void* stream) {
+                                       int flags, int sublattices, const float* act_amax, void* conv_ws, size_t ws_bytes, void* stream) {
     if (!g || !act_amax || !conv_ws) return MVF_ENULL;
     if (B <= 0 || V <= 0 || C <= 0) return MVF_EINVAL;
-    if (C % 64 != 0 || (g->nvox & 1) || (g->nvox_z & 1) || (flags & MVF_FLAG_WORLD_GRID)) return MVF_EUNSUPPORTED;
+    if (C % 64 != 0 || (flags & MVF_FLAG_WORLD_GRID)) return MVF_EUNSUPPORTED;
+    if (sublattices && ((g->nvox & 1) || (g->nvox_z & 1))) return MVF_EUNSUPPORTED;
     if (!aligned16(conv_ws)) return MVF_EALIGN;
     const size_t n1 = (size_t)B * V * g->nvox * g->nvox * g->nvox_z * C;             // elements of the per-view grids
     if (ws_bytes < 4 * n1 + 256) return MVF_EWORKSPACE;                                // [hi n1 halves][lo n1 halves][tail]
@@ -522,5 +525,5 @@ extern "C" int mvf_unproject_split_f16(const float* feats, const float* Rcam, co
     unsigned* tail = (unsigned*)(((uintptr_t)(w0 + 2 * n1) + 15) & ~(uintptr_t)15);
     if (cudaMemcpyAsync(tail, act_amax, 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) return MVF_ECUDA;
     return unproject_impl(feats, Rcam, Rmain, Kmat, g, B, V, fh, fw, C, img_h, img_w, MVF_FUSE_NONE, flags & MVF_FLAG_RELU_IN, 0.0, 0, 0,
-                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (uint2*)w0, (uint2*)(w0 + n1), tail, stream);
+                          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (uint2*)w0, (uint2*)(w0 + n1), tail, sublattices != 0, stream);
 }

@@ -382,9 +382,16 @@ class Conv3dTensorCore:
             self._ws = torch.empty(need // 4, dtype=torch.float32, device=device)
         return self._ws if need else None
 
+    def presplit_workspace(self, B, X, Y, Z, device):
+        """Scratch for operand halves written by ``mvf_unproject_split_f16``: hi + lo fp16 of [B,V,X,Y,Z,C] + the scale cell."""
+        need = 4 * B * self.V * X * Y * Z * self.C + 256
+        if self._ws is None or self._ws.numel() * 4 < need or self._ws.device != device:
+            self._ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=device)
+        return self._ws
+
     def call_presplit(self, B, X, Y, Z, relu_out=True):
-        """Run on operand halves already written into ``self.workspace(...)`` by ``mvf_unproject_split_f16``."""
-        ws = self.workspace(B, X, Y, Z, self.bias.device)
+        """Run on operand halves already written into ``self.presplit_workspace(...)`` by ``mvf_unproject_split_f16``."""
+        ws = self.presplit_workspace(B, X, Y, Z, self.bias.device)
         OX, OY, OZ = self.out_dims(X, Y, Z)
         out = torch.empty((B, OX, OY, OZ, self.Cout), dtype=torch.float32, device=self.bias.device)
         flags = _lib.FLAG_PRESPLIT | (_lib.FLAG_RELU_OUT if relu_out else 0)
@@ -674,11 +681,11 @@ def unproject_unet_fuse(feats, Rcam, Kmat, scope, config, params):
     if Cc % 64 or X % 4 or Z % 4:
         return None
     conv1 = _cached_conv(scope + "_3D_conv_1", params["conv1"], "conv_s2", V=V)
-    ws = conv1.workspace(B, X, X, Z, feats.device)
+    ws = conv1.presplit_workspace(B, X, X, Z, feats.device)
     bound = feats.abs().amax().reshape(1)
     ih, iw = _image_hw(config)
     rc = lib.mvf_unproject_split_f16(_ptr(feats), _ptr(Rcam), None, _ptr(Kmat), C.byref(g), B, V, fh, fw, Cc, ih, iw,
-                                     _lib.FLAG_RELU_IN, _ptr(bound), _ptr(ws), ws.numel() * 4, _stream())
+                                     _lib.FLAG_RELU_IN, 1, _ptr(bound), _ptr(ws), ws.numel() * 4, _stream())
     if rc == _lib.MVF_EUNSUPPORTED:
         return None
     check(rc, "mvf_unproject_split_f16")
@@ -687,6 +694,34 @@ def unproject_unet_fuse(feats, Rcam, Kmat, scope, config, params):
     except ValueError:                                  # the library chose the tf32 format for these channel counts
         return None
     return unet_fuse(None, scope, config, params, conv1_out=c1)
+
+
+def unproject_ident_fuse(feats, Rcam, Kmat, scope, config, params):
+    """``grid_reas(unproj_feat(...))`` for GRID_REAS='ident' (model_multi.py:2382-2392 with :443-455) without materialising the
+    per-view grids: K1 writes ReLU(unprojected views) as the fp16 operand halves of the 1x1x1 convolution, which then runs at
+    the f16 tensor rate (three MMAs per product).  Needs C % 64 == 0; returns None otherwise (caller falls back)."""
+    feats, Rcam, Kmat = _cuda(feats, "feats"), _cuda(Rcam, "Rcam"), _cuda(Kmat, "Kmat")
+    B, V, fh, fw, Cc = feats.shape
+    if Cc % 64:
+        return None
+    g = grid_from_config(config)
+    X, Z = g.nvox, g.nvox_z
+    Wt = _cuda(params["weight"], "weight")
+    Cout = Wt.shape[-1]
+    p = {"W": Wt.reshape(V * Cc, Cout), "b": _cuda(params["bias"], "bias"), "bn": params.get("bn", _default_bn(Cout))}
+    try:
+        conv = _cached_conv(scope + "ident_conv/presplit", p, "conv", V=V, chan_interleave=-1)
+    except ValueError:
+        return None
+    ws = conv.presplit_workspace(B, X, X, Z, feats.device)
+    bound = feats.abs().amax().reshape(1)
+    ih, iw = _image_hw(config)
+    rc = lib.mvf_unproject_split_f16(_ptr(feats), _ptr(Rcam), None, _ptr(Kmat), C.byref(g), B, V, fh, fw, Cc, ih, iw,
+                                     _lib.FLAG_RELU_IN, 0, _ptr(bound), _ptr(ws), ws.numel() * 4, _stream())
+    if rc == _lib.MVF_EUNSUPPORTED:
+        return None
+    check(rc, "mvf_unproject_split_f16")
+    return conv.call_presplit(B, X, X, Z)
 
 
 def fusion_neck(feature_maps, Rcam, Kmat, config, params=None, levels=(2, 3, 4, 5, 6), proj_sizes=None):
@@ -716,7 +751,11 @@ def fusion_neck(feature_maps, Rcam, Kmat, config, params=None, levels=(2, 3, 4, 
             fused = unproject_fuse(fm, Rcam, Kmat, config, mode="sum", bn=gp.get("bn", _default_bn(Cc)), relu_out=True)
             outs.append(proj_grid_depth_sampling([fused, Rcam, Kmat], config, P_, dname, params=dp))
             continue
-        fused = unproject_unet_fuse(fm, Rcam, Kmat, gname, config, gp) if config.GRID_REAS == "conv3d" else None
+        fused = None
+        if config.GRID_REAS == "conv3d":
+            fused = unproject_unet_fuse(fm, Rcam, Kmat, gname, config, gp)
+        elif config.GRID_REAS == "ident" and "weight" in gp:
+            fused = unproject_ident_fuse(fm, Rcam, Kmat, gname, config, gp)
         if fused is None:
             per_view = unproj_feat([fm, Rcam, Kmat], config)
             # bilinear weights are in [0,1] and sum to at most 1, so the unprojected grids are bounded by max|features|: the

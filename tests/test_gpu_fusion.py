@@ -291,3 +291,24 @@ def test_neck_level_host_entry_matches_device_path():
     o_fused = oracle.grid_reas(oracle.unproj_feat(feats, Rcam, Kmat, cfg), "g", small_cfg(GRID_REAS="add"), {"bn": bn})
     o = oracle.depth_sampling(oracle.proj_grid(o_fused, Rcam, Kmat, cfg, P), depth["weight"], depth["bias"], depth["bn"])
     close(h_out.numpy(), o, rtol=1e-5, atol=2e-6)
+
+
+def test_ident_neck_direct_operand_path():
+    """GRID_REAS='ident' with 64-channel features: K1 writes the fp16 operand halves of the 1x1x1 conv directly
+    (mvf_unproject_split_f16 + MVF_FLAG_PRESPLIT); checked against the oracle and against the materialised path."""
+    import mulit_view_object_detection_b200 as m
+    rng = np.random.default_rng(31)
+    B, V, C, F = 2, 3, 64, 48
+    cfg = small_cfg(GRID_REAS="ident", NUM_VIEWS=V, nvox=10, nvox_z=6, TOP_DOWN_PYRAMID_SIZE=F)
+    feats, Rcam, Kmat = scene(cfg, B, V, 20, 20, C, seed=13)
+    params = {"weight": (rng.standard_normal((V * C, F)) * 0.1).astype(np.float32), "bias": rng.normal(0, 0.1, F).astype(np.float32),
+              "bn": random_bn(rng, F)}
+    d = to_dev(feats, Rcam, Kmat)
+    dparams = {"weight": to_dev(params["weight"])[0], "bias": to_dev(params["bias"])[0], "bn": params["bn"]}
+    n0 = m.launch_count()
+    direct = m.unproject_ident_fuse(*d, "grid_reas_P4", cfg, dparams)
+    assert direct is not None and m.launch_count() - n0 <= 4          # weight prep (2), K1, GEMM: no split / amax pass
+    o = oracle.grid_reas(oracle.unproj_feat(feats, Rcam, Kmat, cfg), "grid_reas_P4", cfg, params)
+    close(direct.cpu().numpy(), o, rtol=1e-5, atol=5e-6)
+    mat = m.grid_reas(m.unproj_feat(d, cfg), "grid_reas_P4", cfg, params=dparams)
+    close(direct.cpu().numpy(), mat.cpu().numpy(), rtol=1e-5, atol=5e-6)

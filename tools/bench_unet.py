@@ -93,3 +93,15 @@ print("unproj_feat (per-view grids, %.2f GB): %.3f ms = %.0f GB/s written;  conv
       % (per_view.numel() * 4 / 1e9, ms_k1, per_view.numel() * 4 / ms_k1 / 1e6, ms_neck, tuple(pg[0].shape)))
 if len(sys.argv) > 3:
     json.dump(res, open(sys.argv[3], "w"), indent=1)
+
+# ---- one level of the 'ident' neck: materialised (unproj_feat + 1x1x1 conv with the in-kernel tf32 converter) vs direct (K1 writes
+# the conv's fp16 operand halves)
+icfg = m.FusionConfig(nvox=X, nvox_z=X, samples=S, NUM_VIEWS=V, GRID_REAS="ident", IMAGE_SHAPE=np.array([640, 640, 3]),
+                      TOP_DOWN_PYRAMID_SIZE=F)
+ip = {"weight": rnd(V * C, F, scale=(V * C) ** -0.5), "bias": rnd(F, scale=0.1)}
+ms_mat, _ = timed(lambda: m.grid_reas(m.unproj_feat(d, icfg), "bench_ident", icfg, params=ip))
+ms_dir, _ = timed(lambda: m.unproject_ident_fuse(d[0], d[1], d[2], "bench_ident", icfg, ip))
+res["ident_level_materialised_ms"] = ms_mat; res["ident_level_direct_ms"] = ms_dir
+print("ident level (unproj_feat -> 1x1x1 conv): materialised %.3f ms, direct operand path %.3f ms" % (ms_mat, ms_dir))
+if len(sys.argv) > 3:
+    json.dump(res, open(sys.argv[3], "w"), indent=1)
