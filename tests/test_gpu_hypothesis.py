@@ -149,3 +149,30 @@ def test_random_tensor_core_convolutions(case):
     ref = (ref + b).astype(np.float32)
     assert got.shape == ref.shape
     close(got, ref, rtol=1e-5, atol=5e-6)
+
+
+@settings(max_examples=12, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(st.integers(0, 2 ** 31 - 1), st.sampled_from([32, 64, 96, 128]), st.integers(1, 5), st.integers(1, 5), st.integers(1, 9),
+       st.sampled_from([(0, 0), (1, 0), (0, 1), (1, 1)]))
+def test_random_convlstm_slab_steps(seed, C, X, Y, Z, halo):
+    """mvf_convlstm_step_tc_slab over random slab shapes, halo combinations and both operand-split formats (C % 64): the slab
+    step on a padded input equals the oracle's full SAME convolution on the same padded extent, restricted to the interior."""
+    m = _m()
+    rng = np.random.default_rng(seed)
+    F = 64 * ((C + 63) // 64) if C % 64 else C              # F must be a multiple of 64; C may be 32 / 96 (tf32 split)
+    lo, hi = halo
+    Xin = X + lo + hi
+    W = (rng.standard_normal((3, 3, 3, C + F, 4 * F)) * np.sqrt(2.0 / (27 * (C + F) + 4 * F))).astype(np.float32)
+    b = rng.normal(0, 0.1, 4 * F).astype(np.float32)
+    x = rng.standard_normal((1, Xin, Y, Z, C)).astype(np.float32)
+    hp = np.tanh(rng.standard_normal((1, Xin, Y, Z, F))).astype(np.float32) * 0.5
+    cp = rng.standard_normal((1, X, Y, Z, F)).astype(np.float32)
+    cell = m.ConvLSTMTensorCore(*to_dev(W, b), 1.0)
+    h, c = cell.step_slab(*to_dev(x, hp, cp), (lo, hi), relu_in=True)
+    cpad = np.zeros((1, Xin, Y, Z, F), np.float32)
+    cpad[:, lo:lo + X] = cp
+    # the oracle pads with zeros on every side; planes next to a halo see the halo data, planes at a missing halo see zeros:
+    # exactly what the slab kernel reads (TMA zero fill beyond the tensor)
+    oh, oc = oracle.convlstm_cell_step(np.maximum(x, 0), cpad, hp, W, b)
+    close(h.cpu().numpy()[:, lo:lo + X], oh[:, lo:lo + X], rtol=1e-5, atol=3e-6)
+    close(c.cpu().numpy(), oc[:, lo:lo + X], rtol=1e-5, atol=3e-6)
