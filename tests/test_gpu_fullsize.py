@@ -107,3 +107,46 @@ def test_batched_scenes_equal_single_scene_calls():
     for b in (0, 3, 4):
         r1, f1 = m.unproject_fuse_project(d[0][b:b + 1], d[1][b:b + 1], d[2][b:b + 1], cfg, T["P"], mode="sum")
         assert torch.equal(f1[0], fused[b]) and torch.equal(r1[0], rays[b])
+
+
+def test_config_c1_against_the_oracle():
+    """BASELINE.json configs[0]: 2-view scene, 256-ch 60x80 P4 features, 32^3 grid, fp32 unproject -> mean-fuse -> project, at
+    its full size against the NumPy oracle (the reference's CPU-runnable case): indices / masks / ray voxels bit-exact,
+    features and ray slices within 1e-5.  The non-square map takes the (60, 80) generalisation of proj_grid."""
+    m = _m()
+    cfg = small_cfg(nvox=32, nvox_z=32, samples=20, NUM_VIEWS=2, IMAGE_SHAPE=np.array([480, 640, 3]))
+    feats, Rcam, Kmat = scene(cfg, 1, 2, 60, 80, 256, seed=1001, image_hw=(480, 640))
+    d = to_dev(feats, Rcam, Kmat)
+    per_view, idx, valid = m.unproj_feat(d, cfg, return_aux=True)
+    o_views, o_idx, o_valid = oracle.unproj_feat(feats, Rcam, Kmat, cfg, return_aux=True)
+    assert np.array_equal(idx.cpu().numpy(), o_idx) and np.array_equal(valid.cpu().numpy(), o_valid)
+    np.testing.assert_allclose(per_view.cpu().numpy(), o_views, rtol=1e-5, atol=1e-6)
+    rays, fused = m.unproject_fuse_project(*d, cfg, (60, 80), mode="mean")
+    o_fused = oracle.fuse_views(o_views, "mean")
+    np.testing.assert_allclose(fused.cpu().numpy(), o_fused, rtol=1e-5, atol=1e-6)
+    _, vox, pvalid = m.proj_grid([fused, d[1], d[2]], cfg, (60, 80), return_aux=True)
+    o_vox, o_pvalid = oracle.project_indices(Rcam, Kmat, cfg, (60, 80))
+    assert np.array_equal(vox.cpu().numpy(), o_vox) and np.array_equal(pvalid.cpu().numpy().astype(bool), o_pvalid.astype(bool))
+    o_rays = oracle.proj_grid(o_fused, Rcam, Kmat, cfg, (60, 80))
+    assert rays.shape == o_rays.shape == (1, 20, 60, 80, 256)
+    np.testing.assert_allclose(rays.cpu().numpy(), o_rays, rtol=1e-5, atol=1e-6)
+    assert float(np.abs(o_rays).max()) > 0 and (o_valid != 0).mean() > 0.3
+
+
+def test_config_c2_fusion_against_the_oracle():
+    """BASELINE.json configs[1], fusion part at the P4 level: 4 views, 256-ch 40x40 features (640x640 padded input), 48^3 grid,
+    max-fuse + projection, full size against the oracle (max is a selection: fused grid within 1e-5 of the oracle's, rays a
+    bit-exact gather of our own grid); the ROIAlign / NMS halves of c2 run at 1000 / 6000 boxes in test_gpu_heads.py."""
+    import torch
+    m = _m()
+    cfg = small_cfg(nvox=48, nvox_z=48, samples=20, NUM_VIEWS=4, IMAGE_SHAPE=np.array([640, 640, 3]))
+    feats, Rcam, Kmat = scene(cfg, 1, 4, 40, 40, 256, seed=2001)
+    d = to_dev(feats, Rcam, Kmat)
+    rays, fused = m.unproject_fuse_project(*d, cfg, 40, mode="max")
+    o_views, o_idx, o_valid = oracle.unproj_feat(feats, Rcam, Kmat, cfg, return_aux=True)
+    o_fused = oracle.fuse_views(o_views, "max")
+    np.testing.assert_allclose(fused.cpu().numpy(), o_fused, rtol=1e-5, atol=1e-6)
+    _, idx, valid = m.unproj_feat(d, cfg, return_aux=True)
+    assert np.array_equal(idx.cpu().numpy(), o_idx) and np.array_equal(valid.cpu().numpy(), o_valid)
+    o_rays = oracle.proj_grid(fused.cpu().numpy(), Rcam, Kmat, cfg, 40)
+    assert np.array_equal(rays.cpu().numpy(), o_rays)
