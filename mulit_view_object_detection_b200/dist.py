@@ -279,3 +279,17 @@ def lstm_slab(feats, Rcam, Kmat, config, params, proj_size=None, group=None, ops
     rays = ops.proj_grid(slab, Rcam, Kmat, config, proj_size, x_slab=(xb, xc))
     rays = _all_reduce(rays, dist.ReduceOp.SUM, group)
     return rays, slab
+
+
+def fuse_project_auto(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None):
+    """Pick the sharding that moves the fewest bytes (measured in profiles/r1_scaling.json): enough scenes
+    for every rank -> ``scene_shard`` (no exchange at all; rays gathered back into scene order); fewer scenes than ranks ->
+    ``slab_owner`` (features replicated, one all-reduce of the ray slices).  View sharding is never chosen: its partial grids
+    cross NVLink (25 GB per rank at config c5) and it is slower than one GPU.  Returns the full ray slices [B,S,P,P,C]."""
+    rank, ws = world(group)
+    B = feats.shape[0]
+    if ws == 1 or (B >= ws and B % ws == 0):
+        rays, _ = scene_shard(feats, Rcam, Kmat, config, proj_size, mode=mode, group=group, ops=ops, gather=True)
+        return rays
+    rays, _ = slab_owner(feats, Rcam, Kmat, config, proj_size, mode=mode, group=group, ops=ops)
+    return rays

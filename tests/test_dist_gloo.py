@@ -91,6 +91,10 @@ def _worker(rank, world_size, port, strategy, mode, out_dir):
         ops = OracleOps()
         if strategy == "scene":
             rays, mine = mvd.scene_shard(*t, cfg, 10, mode=mode, ops=ops, gather=True)
+        elif strategy == "auto":
+            rays = mvd.fuse_project_auto(*t, cfg, 10, mode=mode, ops=ops)                       # 2 scenes, 2 ranks: scene sharding
+            one = mvd.fuse_project_auto(*[x[:1] for x in t], cfg, 10, mode=mode, ops=ops)         # 1 scene, 2 ranks: slab owner
+            assert torch.allclose(one, rays[:1], rtol=1e-5, atol=1e-6)
         elif strategy == "slab_owner_scatter":
             part, _ = mvd.slab_owner(*t, cfg, 10, mode=mode, ops=ops, scatter_scenes=True)   # rank r keeps scene r
             parts = [torch.empty_like(part) for _ in range(world_size)]
@@ -146,7 +150,7 @@ def test_lstm_slab_halo_exchange_matches_single_process(world_size, tmp_path):
 @pytest.mark.parametrize("strategy,mode", [("allreduce", "sum"), ("allreduce", "max"), ("allreduce", "mean"),
                                            ("reduce_scatter", "sum"), ("reduce_scatter", "max"),
                                            ("slab_owner", "sum"), ("slab_owner", "max"), ("scene", "sum"),
-                                           ("slab_owner_scatter", "sum")])
+                                           ("slab_owner_scatter", "sum"), ("auto", "sum")])
 def test_two_rank_strategies_match_single_process(strategy, mode, tmp_path):
     world_size = 2
     mp.spawn(_worker, args=(world_size, _free_port(), strategy, mode, str(tmp_path)), nprocs=world_size, join=True)
