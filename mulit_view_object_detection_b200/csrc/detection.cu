@@ -233,12 +233,14 @@ nms_scan_kernel(const unsigned* mask, const int32_t* s_idx, const int32_t* s_cls
             nidx = (wi + 1 < nwords && row < n) ? ip[row] : -1;
             ncls = (wi + 1 < nwords && row < n) ? cp[row] : -1;
             unsigned cur = sh_cur, kept = 0;
-            int done = 0;
+            const unsigned present = __ballot_sync(0xffffffffu, idx >= 0);     // candidates of this block (a prefix of the lanes)
+            int done = present != 0xffffffffu;                                 // a short block is the last one
+            unsigned alive = present & ~cur;                                   // visit only candidates that are not suppressed yet
 #pragma unroll 1
-            for (int b = 0; b < 32; ++b) {
-                const int bi = __shfl_sync(0xffffffffu, idx, b);
-                if (bi < 0 || total >= max_total) { done = 1; break; }    // past the last candidate / output full
-                if ((cur >> b) & 1u) continue;
+            while (alive) {
+                if (total >= max_total) { done = 1; break; }                   // output full
+                const int b = __ffs(alive) - 1;
+                alive &= ~(1u << b);
                 if (!single_class) {
                     const int c = __shfl_sync(0xffffffffu, cls, b);
                     const int cnt = sh_cnt[c];                                // broadcast read
@@ -247,10 +249,12 @@ nms_scan_kernel(const unsigned* mask, const int32_t* s_idx, const int32_t* s_cls
                     if (lane == 0) sh_cnt[c] = cnt + 1;
                     __syncwarp();
                 }
+                const int bi = __shfl_sync(0xffffffffu, idx, b);
                 if (lane == 0) kp[total] = by_position ? (wi * 32 + b) : bi;
                 ++total;
                 kept |= 1u << b;
                 cur |= __shfl_sync(0xffffffffu, diag, b);
+                alive &= ~cur;
             }
             if (total >= max_total) done = 1;
             if (lane == 0) { sh_total = total; sh_kept = kept; sh_done = done; }
