@@ -214,6 +214,52 @@ def convlstm_line(dev):
             "checksum": float(h2.double().sum())}
 
 
+def c2_line(dev, peak):
+    """Config c2 extras (4-view scene, 48^3 grid, max-fuse + PyramidROIAlign + NMS on one B200): device-resident timings of the
+    head kernels and of the max-fuse pipeline at the P4 level, CUDA events over 20 back-to-back calls each."""
+    import torch
+    import mulit_view_object_detection_b200 as m
+    from mulit_view_object_detection_b200 import synthetic as syn
+    rng = np.random.default_rng(2000)
+    C, img = 256, 640
+    cfg = m.FusionConfig(nvox=48, nvox_z=48, samples=20, NUM_VIEWS=4, GRID_REAS="max", IMAGE_SHAPE=np.array([img, img, 3]))
+
+    def timed(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    maps = [torch.from_numpy(np.maximum(rng.standard_normal((1, img // s, img // s, C), dtype=np.float32), 0)).to(dev) for s in (4, 8, 16, 32)]
+    meta = syn.make_image_meta(1, (img, img, 3), 25)
+    boxes = torch.from_numpy(syn.make_rois(rng, 1, 1000)).to(dev)
+    roi = m.PyramidROIAlign([7, 7])
+    b6 = torch.from_numpy(syn.make_rois(rng, 1, 6000, pad_frac=0)[0]).to(dev)
+    s6 = torch.from_numpy(rng.permutation(6000).astype(np.float32) / 6000).to(dev)
+    probs, deltas = syn.make_detection_inputs(rng, 1000, 25)
+    det = [torch.from_numpy(a).to(dev) for a in (syn.make_rois(rng, 1, 1000)[0], probs, deltas)]
+    window = torch.tensor([0.0, 0.0, 1.0, 1.0], device=dev)
+    feats, Rcam, Kmat = syn.make_scene(cfg, 1, 4, 40, 40, C, seed=2001)
+    d = [torch.from_numpy(a).to(dev) for a in (feats, Rcam, Kmat)]
+    grid = torch.empty((1, 48, 48, 48, C), device=dev)
+    rays = torch.empty((1, 20, 40, 40, C), device=dev)
+    ms_roi = timed(lambda: roi([boxes, meta] + maps))
+    ms_fuse = timed(lambda: m.unproject_fuse_project(*d, cfg, 40, mode="max", grid_out=grid, out=rays))
+    lower = 4 * C * 1000 * 49 * 2
+    return {"workload": "c2: 4 views, 48^3, max-fuse + projection at P4 (one scene); PyramidROIAlign 1000x7x7x256; NMS of 6000 boxes; "
+                        "refine_detections 1000x25 (timings include the Python/ctypes launch path)",
+            "fusion_max_P4_ms": ms_fuse, "fusion_voxel_samples_per_s": 4 * 48 ** 3 / ms_fuse * 1e3,
+            "roi_align_1000x7x7_ms": ms_roi, "roi_align_frac_of_hbm_peak_vs_2_vectors_per_bin": lower / ms_roi / 1e6 / peak,
+            "nms_6000_boxes_ms": timed(lambda: m.non_max_suppression(b6, s6, 1000, 0.7)),
+            "refine_detections_1000x25_ms": timed(lambda: m.refine_detections_graph(det[0], det[1], det[2], window, cfg))}
+
+
 # ---------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -349,6 +395,7 @@ def run_b200(args):
         }
         if world == 1 and not args.no_convlstm:
             line["k2_convlstm"] = convlstm_line(dev)
+            line["c2_heads"] = c2_line(dev, peak)
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = 24
             v, s_per, threads = cpu_reference_run(1, 16, n_cpu, 1)
