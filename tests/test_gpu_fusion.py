@@ -312,3 +312,31 @@ def test_ident_neck_direct_operand_path():
     close(direct.cpu().numpy(), o, rtol=1e-5, atol=5e-6)
     mat = m.grid_reas(m.unproj_feat(d, cfg), "grid_reas_P4", cfg, params=dparams)
     close(direct.cpu().numpy(), mat.cpu().numpy(), rtol=1e-5, atol=5e-6)
+
+
+@pytest.mark.parametrize("nvox,nvox_z,C,V", [(7, 9, 36, 3), (16, 16, 256, 8), (5, 3, 4, 1)])
+def test_kernels_write_only_their_output(nvox, nvox_z, C, V):
+    """Guard bands around the outputs of K1 and K3 (ragged grids, channel counts that are not a multiple of the warp tile):
+    nothing outside [out, out + numel) is written."""
+    import mulit_view_object_detection_b200 as m
+    cfg = small_cfg(nvox=nvox, nvox_z=nvox_z, samples=5, NUM_VIEWS=V)
+    feats, Rcam, Kmat = scene(cfg, 2, V, 11, 13, C, seed=3)
+    d = to_dev(feats, Rcam, Kmat)
+    G, SENT = 4096, 12345.0
+
+    def guarded(shape):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * G,), SENT, device="cuda")
+        return buf, buf[G:G + n].view(shape)
+
+    for mode, shape in (("sum", (2, nvox, nvox, nvox_z, C)), ("max", (2, nvox, nvox, nvox_z, C)), ("none", (2, V, nvox, nvox, nvox_z, C))):
+        buf, out = guarded(shape)
+        m.unproject_fuse(*d, cfg, mode=mode, out=out)
+        torch.cuda.synchronize()
+        assert bool((buf[:G] == SENT).all()) and bool((buf[-G:] == SENT).all()), mode
+        assert bool((out != SENT).all())                       # and every output element was written
+    fused = m.unproject_fuse(*d, cfg, mode="sum")
+    buf, rays = guarded((2, 5, 9, 6, C))
+    m.proj_grid([fused, d[1], d[2]], cfg, (9, 6), out=rays)
+    torch.cuda.synchronize()
+    assert bool((buf[:G] == SENT).all()) and bool((buf[-G:] == SENT).all()) and bool((rays != SENT).all())
