@@ -529,10 +529,16 @@ weight_split_kernel(const float* __restrict__ W, float* __restrict__ whi, float*
 // max-reduction pass, no host sync) keeps a1 below 2^14 and pushes a2 well into the normal fp16 range; the GEMM epilogue
 // multiplies by 2^-(s_a + s_w).
 __global__ void __launch_bounds__(256)
-amax_kernel(const float4* __restrict__ in, long long n4, int relu, unsigned* __restrict__ amax_bits) {
+amax_kernel(const float4* __restrict__ in, long long n4, int relu, unsigned* __restrict__ amax_bits,
+            const float4* __restrict__ pre_scale = nullptr, const float4* __restrict__ pre_shift = nullptr, long long inner4 = 1, int V = 1, int C4 = 1) {
     float m = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 v = __ldg(in + i);
+        if (pre_scale) {                                  // per-input-channel affine (depthwise 1x1) in front of the conv: channel (v, c)
+            const int ch = (int)((i / inner4) % V) * C4 + (int)(i % C4);
+            const float4 sc = __ldg(pre_scale + ch), sh = __ldg(pre_shift + ch);
+            v = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+        }
         if (relu) v = relu4(v);
         m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
@@ -543,13 +549,19 @@ amax_kernel(const float4* __restrict__ in, long long n4, int relu, unsigned* __r
 // activations: same indexing as act_split_kernel (optional ReLU, optional parity sub-lattice re-layout); tail[0] = amax bits, tail[1] <- 2^-s
 __global__ void __launch_bounds__(256)
 act_split_f16_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint2* __restrict__ lo, long long n4,
-                     int X, int Y, int Z, int C4, int relu, int s2d, unsigned* __restrict__ tail) {
+                     int X, int Y, int Z, int C4, int relu, int s2d, unsigned* __restrict__ tail,
+                     const float4* __restrict__ pre_scale = nullptr, const float4* __restrict__ pre_shift = nullptr, int V = 1) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float inv;
     const float scale = pow2_scale(tail[0], &inv);
     if (i == 0) reinterpret_cast<float*>(tail)[1] = inv;
     if (i >= n4) return;
     float4 v = __ldg(in + i);
+    if (pre_scale) {
+        const int ch = (int)((i / ((long long)X * Y * Z * C4)) % V) * C4 + (int)(i % C4);
+        const float4 sc = __ldg(pre_scale + ch), sh = __ldg(pre_shift + ch);
+        v = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+    }
     if (relu) v = relu4(v);
     long long o = i;
     if (s2d) {
@@ -569,7 +581,7 @@ act_split_f16_kernel(const float4* __restrict__ in, uint2* __restrict__ hi, uint
 // (row n' = (f / 64) * 256 + gate * 64 + f % 64  <-  column gate * F + f, F = N / 4)
 __global__ void __launch_bounds__(256)
 weight_split_f16_kernel(const float* __restrict__ W, __half* __restrict__ whi, __half* __restrict__ wlo, int K, int N, int mode, int Cin,
-                        unsigned* __restrict__ tail) {
+                        unsigned* __restrict__ tail, int S = 1) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // output element, k fastest
     float inv;
     const float scale = pow2_scale(tail[0], &inv);
@@ -579,6 +591,7 @@ weight_split_f16_kernel(const float* __restrict__ W, __half* __restrict__ whi, _
     long long src;
     if (mode == 1) { const int tap = k / Cin, ci = k - tap * Cin; src = ((long long)tap * N + n) * Cin + ci; }
     else if (mode == 2) { const int F = N / 4, grp = n / TC_N, gate = (n % TC_N) / TC_FPT, fl = n % TC_FPT; src = (long long)k * N + gate * F + grp * TC_FPT + fl; }
+    else if (mode == 3) { const int tap = k / Cin, r = k - tap * Cin, Cc = Cin / S, sidx = r / Cc, c = r - sidx * Cc; src = ((long long)tap * Cin + c * S + sidx) * N + n; }   // row s*C+c <- reference row c*S+s
     else src = (long long)k * N + n;
     const float v = W[src] * scale;
     const __half a1 = __float2half_rn(v);
@@ -771,7 +784,8 @@ static int conv_taps(int kind, int ksize) { return (kind == MVF_CONV_S1 && ksize
 
 extern "C" size_t mvf_conv3d_wsplit_bytes(int kind, int ksize, int Cin, int Cout) {
     if (Cin <= 0 || Cout <= 0 || (ksize != 1 && ksize != 3)) return 0;
-    return (size_t)2 * conv_taps(kind, ksize) * Cin * Cout * sizeof(float) + 256;
+    // k = 1: both operand formats (tf32 for the fused converter, fp16 for the split-pass path, chosen per call); k = 3: one of them
+    return (size_t)(ksize == 1 ? 3 : 2) * conv_taps(kind, ksize) * Cin * Cout * sizeof(float) + 512;
 }
 
 static bool conv3d_f16(int ksize, int C, int C2, bool pre_affine) { return ksize == 3 && !pre_affine && want_f16(C, C2); }
@@ -803,6 +817,15 @@ extern "C" int mvf_conv3d_prepare(const float* W, int kind, int ksize, int V, in
     weight_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, wsplit, wsplit + total, K, Cout,
                                                                       kind == MVF_DECONV_S2, Cin, chan_interleave);
     count_launch();
+    if (ksize == 1 && want_f16(C, C2)) {                  // second copy for small 1x1x1 problems, which take the split-pass path at the f16 rate
+        __half* whi = (__half*)(wsplit + 2 * total);
+        unsigned* tail = (unsigned*)(whi + 2 * total);
+        if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
+        amax_kernel<<<amax_grid(total / 4), 256, 0, s>>>((const float4*)W, total / 4, 0, tail);
+        weight_split_f16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(W, whi, whi + total, K, Cout, chan_interleave > 1 ? 3 : 0, Cin, tail,
+                                                                               chan_interleave > 1 ? chan_interleave : 1);
+        count_launch(2);
+    }
     return check_launch();
 }
 
@@ -851,7 +874,10 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     if (!encode_tiled()) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
     const long long n1 = (long long)B * V * X * Y * Z * C, n2 = (long long)B * X * Y * Z * C2;
-    const bool f16 = presplit ? conv3d_f16_presplit(C, C2) : (split_pass && conv3d_f16(ksize, C, C2, pre_scale != nullptr));
+    // k = 3: fp16 halves whenever the channel counts allow; k = 1 on the split-pass path (small problems): the fp16 copy of the
+    // weights that mvf_conv3d_prepare wrote behind the tf32 one (with the depthwise affine applied by the split pass)
+    const bool f16_k1 = !presplit && split_pass && ksize == 1 && want_f16(C, C2);
+    const bool f16 = presplit ? conv3d_f16_presplit(C, C2) : (f16_k1 || (split_pass && conv3d_f16(ksize, C, C2, pre_scale != nullptr)));
     if (presplit && (!f16 || !ws || ws_bytes < 4 * (size_t)n1 + 256)) return presplit && !f16 ? MVF_EUNSUPPORTED : MVF_EWORKSPACE;
     const void *xh = in, *xl = in, *hh = in2, *hl = in2;
     const float* inv_a = nullptr;
@@ -866,11 +892,13 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
             if (cudaMemcpyAsync(tail, act_amax, 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return MVF_ECUDA;
         } else {
             if (cudaMemsetAsync(tail, 0, 8, s) != cudaSuccess) return MVF_ECUDA;
-            amax_kernel<<<amax_grid(n1 / 4), 256, 0, s>>>((const float4*)in, n1 / 4, relu_in, tail);
+            amax_kernel<<<amax_grid(n1 / 4), 256, 0, s>>>((const float4*)in, n1 / 4, relu_in, tail, (const float4*)pre_scale, (const float4*)pre_shift,
+                                                          (long long)X * Y * Z * (C / 4), V, C / 4);
             if (in2) amax_kernel<<<amax_grid(n2 / 4), 256, 0, s>>>((const float4*)in2, n2 / 4, relu_in, tail);  // sources share the accumulator: one scale
             count_launch(in2 ? 2 : 1);
         }
-        act_split_f16_kernel<<<(unsigned)((n1 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (uint2*)w0, (uint2*)w1, n1 / 4, X, Y, Z, C / 4, relu_in, s2d, tail);
+        act_split_f16_kernel<<<(unsigned)((n1 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in, (uint2*)w0, (uint2*)w1, n1 / 4, X, Y, Z, C / 4, relu_in, s2d, tail,
+                                                                            (const float4*)pre_scale, (const float4*)pre_shift, V);
         if (in2) act_split_f16_kernel<<<(unsigned)((n2 / 4 + 255) / 256), 256, 0, s>>>((const float4*)in2, (uint2*)w2, (uint2*)w3, n2 / 4, X, Y, Z, C2 / 4, relu_in, s2d, tail);
         count_launch(in2 ? 2 : 1);
         xh = w0; xl = w1; hh = w2; hl = w3;
@@ -913,7 +941,10 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     const long long wtotal = (long long)K * Cout;
     const void *whi = wsplit, *wlo = wsplit + wtotal;
     a.inv_scale_a = inv_a; a.inv_scale_w = nullptr;
-    if (f16) { wlo = (const __half*)wsplit + wtotal; a.inv_scale_w = (const float*)((const __half*)wsplit + 2 * wtotal) + 1; }
+    if (f16) {
+        const __half* w16 = f16_k1 ? (const __half*)(wsplit + 2 * wtotal) : (const __half*)wsplit;      // k = 1: behind the tf32 copy
+        whi = w16; wlo = w16 + wtotal; a.inv_scale_w = (const float*)(w16 + 2 * wtotal) + 1;
+    }
     CUtensorMap tm_xh, tm_xl, tm_hh, tm_hl, tm_wh, tm_wl;
     bool ok = make_act_map(&tm_xh, xh, B * V * nb_mul, MX, MY, MZ, C, a.BX, a.BY, a.BZ, f16) &&
               make_act_map(&tm_xl, xl, B * V * nb_mul, MX, MY, MZ, C, a.BX, a.BY, a.BZ, f16) &&
