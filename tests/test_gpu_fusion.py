@@ -340,3 +340,45 @@ def test_kernels_write_only_their_output(nvox, nvox_z, C, V):
     m.proj_grid([fused, d[1], d[2]], cfg, (9, 6), out=rays)
     torch.cuda.synchronize()
     assert bool((buf[:G] == SENT).all()) and bool((buf[-G:] == SENT).all()) and bool((rays != SENT).all())
+
+
+def test_hot_cell_known_answer():
+    """Known answer: features that are 1 on the four pixels of ONE bilinear cell and 0 elsewhere.  A voxel
+    that projects into that cell samples exactly its four pixels, so its value is the weight sum 1; a voxel whose cell shares
+    no pixel with it gets exactly 0; nothing exceeds 1.  Independent of the oracle's bilinear arithmetic."""
+    import mulit_view_object_detection_b200 as m
+    cfg = small_cfg(nvox=24, nvox_z=24, NUM_VIEWS=2)
+    feats, Rcam, Kmat = scene(cfg, 1, 2, 40, 40, 8, seed=5)
+    d = to_dev(feats, Rcam, Kmat)
+    _, idx, valid = m.unproj_feat(d, cfg, return_aux=True)
+    idx, valid = idx.cpu().numpy()[0], valid.cpu().numpy()[0]                   # [V,X,Y,Z,2] (y0,x0), [V,X,Y,Z]
+    full = valid[0] == 15
+    cells, counts = np.unique(idx[0][full].reshape(-1, 2), axis=0, return_counts=True)
+    y0, x0 = cells[np.argmax(counts)]                                          # the most populated interior cell of view 0
+    hot = np.zeros_like(feats)
+    hot[0, 0, y0:y0 + 2, x0:x0 + 2, :] = 1.0
+    out = m.unproj_feat([to_dev(hot)[0], d[1], d[2]], cfg).cpu().numpy()[0, 0]    # view 0 grid [X,Y,Z,C]
+    in_cell = full & (idx[0][..., 0] == y0) & (idx[0][..., 1] == x0)
+    assert in_cell.sum() > 0
+    assert np.abs(out[in_cell] - 1.0).max() <= 4e-7
+    far = (np.abs(idx[0][..., 0] - y0) > 1) | (np.abs(idx[0][..., 1] - x0) > 1)
+    assert np.all(out[far] == 0.0)
+    assert out.max() <= 1.0 + 4e-7 and out.min() >= 0.0
+
+
+def test_constant_field_round_trip_known_answer():
+    """Known answer: unproject a constant field from the main view only, then project back: a ray sample
+    reads 1 where its voxel lies inside the grid AND all four taps of that voxel are inside the view-0 map, 0 outside the grid."""
+    import mulit_view_object_detection_b200 as m
+    cfg = small_cfg(nvox=20, nvox_z=20, samples=9, NUM_VIEWS=1)
+    feats, Rcam, Kmat = scene(cfg, 1, 1, 40, 40, 4, seed=2)
+    d = to_dev(np.ones_like(feats), Rcam, Kmat)
+    per_view, _, valid = m.unproj_feat(d, cfg, return_aux=True)
+    rays, vox, pvalid = m.proj_grid([per_view[:, 0].contiguous(), d[1], d[2]], cfg, 20, return_aux=True)
+    rays, vox, pvalid, valid = rays.cpu().numpy()[0], vox.cpu().numpy()[0], pvalid.cpu().numpy()[0].astype(bool), valid.cpu().numpy()[0, 0]
+    assert np.all(rays[~pvalid] == 0.0)                                        # outside the grid: zero fill
+    v = vox[pvalid]
+    tap_bits = valid[v[:, 0], v[:, 1], v[:, 2]]
+    inside = rays[pvalid][tap_bits == 15]
+    assert inside.size > 0 and np.abs(inside - 1.0).max() <= 4e-7              # inside the frustum: the constant comes back
+    assert np.all(rays[pvalid][tap_bits == 0] == 0.0)                          # voxels the view does not see
