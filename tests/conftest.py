@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The C-ABI library is a build artefact (git-ignored): in a fresh checkout build it once (nvcc cross-compiles sm_100a
+    # without a GPU), so that the ABI / host-logic tests do not depend on a previous manual build.
+    lib = os.path.join(ROOT, "mulit_view_object_detection_b200", "libmvfusion.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def pytest_collection_modifyitems(config, items):
