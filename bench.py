@@ -148,23 +148,34 @@ def cpu_reference_run(scenes, slab, steps, warmup, threads=None):
 
 
 def run_reference(args):
+    """CPU arm: the reference's algorithm on the host cores.  Imports only the pure-host modules of the package (config,
+    synthetic) and oracle/ -- libmvfusion.so is never mapped and no GPU is touched in this process."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     slab = 16
-    value, s_per_step, threads = cpu_reference_run(1, slab, args.steps, min(args.warmup, 1))
+    warmup = max(args.warmup, 3)
+    value, s_per_step, threads = cpu_reference_run(1, slab, args.steps, warmup)
     sample = "1 scene of workload T restricted to an x-slab of %d/64 planes (%d voxel-samples per step) + full proj_grid" \
              % (slab, T["V"] * slab * 64 * 64)
+    cfgd = workload_config(args, args.gpus)
+    cfgd["workload"] += " -- CPU arm: bounded sample per step = " + sample
+    cfgd["scenes_per_gpu"] = 1
+    cfgd["sample_x_planes"] = slab
+    cfgd["sharding"] = "rank 0 only, host cores"
+    cfgd["l2_policy"] = "n/a (CPU arm)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": s_per_step * 1e3,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": s_per_step * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, args.gpus),
+            "config": cfgd,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
+            "native_library_loaded": any("libmvfusion" in l for l in open("/proc/self/maps")) if os.path.exists("/proc/self/maps") else None,
             "note": "TensorFlow/Keras are not installable here (no wheel, no network) and TF-CPU gather_nd raises on this "
                     "path's out-of-range taps; this arm times oracle/torch_cpu.py, the op-for-op torch-CPU port of the "
-                    "reference graph, on all host threads"}
+                    "reference graph (pinned bit for bit to the NumPy oracle and the reference-generated fixtures by "
+                    "tests/test_oracle_torch_cpu.py), on all host threads"}
     print(json.dumps(line))
     return 0
 

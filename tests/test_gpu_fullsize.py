@@ -150,3 +150,51 @@ def test_config_c2_fusion_against_the_oracle():
     assert np.array_equal(idx.cpu().numpy(), o_idx) and np.array_equal(valid.cpu().numpy(), o_valid)
     o_rays = oracle.proj_grid(fused.cpu().numpy(), Rcam, Kmat, cfg, 40)
     assert np.array_equal(rays.cpu().numpy(), o_rays)
+
+
+# ---- feature VALUES at full size against the CPU oracle -------------------------------------------------------------------------
+# oracle/torch_cpu.py is pinned bit for bit to the NumPy oracle and to the reference-generated golden fixtures by
+# tests/test_oracle_torch_cpu.py; it does a quarter slab of workload T in well under a second per mode.
+# Tolerance: north_star's 1e-5 relative for fused features (K1 sums FMA chains, the reference sums four rounded products, then the
+# views); atol 1e-6 covers elements that cancel to ~0.  Ray slices are a pure gather of the fused grid, so the same bar applies.
+@pytest.mark.parametrize("mode", ["sum", "mean", "max"])
+def test_workload_T_features_against_the_oracle(mode):
+    import torch
+    from oracle import torch_cpu
+    m = _m()
+    cfg = _cfg()
+    feats, Rcam, Kmat = scene(cfg, 1, T["V"], T["fh"], T["fw"], T["C"], seed=1000)
+    d = to_dev(feats, Rcam, Kmat)
+    rays, fused = m.unproject_fuse_project(*d, cfg, T["P"], mode=mode)
+    fused_h = fused.cpu()
+    o_fused = torch.empty_like(fused_h)
+    for xb in range(0, T["nvox"], 16):                                        # four quarter slabs = the full scene
+        o_fused[:, xb:xb + 16] = torch_cpu.unproject_fuse(feats, Rcam, Kmat, cfg, mode, x_slab=(xb, 16))
+    np.testing.assert_allclose(fused_h.numpy(), o_fused.numpy(), rtol=1e-5, atol=1e-6)
+    assert (o_fused != 0).float().mean().item() > 0.3
+    o_rays = torch_cpu.project(o_fused, Rcam, Kmat, cfg, T["P"])
+    np.testing.assert_allclose(rays.cpu().numpy(), o_rays.numpy(), rtol=1e-5, atol=1e-6)
+    assert (o_rays != 0).any()
+
+
+def test_c5_grid_slab_against_the_oracle():
+    """Config c5's grid (96^3, 8 views, 256 channels): one 12-plane x-slab of the fused grid -- the unit the reduce-scatter /
+    slab-owner layouts hand to each rank -- and the ray slices that slab contributes, against the CPU oracle."""
+    import torch
+    from oracle import torch_cpu
+    m = _m()
+    cfg = _cfg(96)
+    feats, Rcam, Kmat = scene(cfg, 1, T["V"], T["fh"], T["fw"], T["C"], seed=5000)
+    d = to_dev(feats, Rcam, Kmat)
+    xb, xc = 36, 12
+    slab = m.unproject_fuse(*d, cfg, mode="sum", x_slab=(xb, xc))
+    o_slab = torch_cpu.unproject_fuse(feats, Rcam, Kmat, cfg, "sum", x_slab=(xb, xc))
+    np.testing.assert_allclose(slab.cpu().numpy(), o_slab.numpy(), rtol=1e-5, atol=1e-6)
+    assert (o_slab != 0).float().mean().item() > 0.3
+    # the slab's share of the ray slices: project a grid that is zero outside the slab
+    rays = m.proj_grid([slab, d[1], d[2]], cfg, T["P"], x_slab=(xb, xc))
+    o_full = torch.zeros((1, 96, 96, 96, T["C"]))
+    o_full[:, xb:xb + xc] = o_slab
+    o_rays = torch_cpu.project(o_full, Rcam, Kmat, cfg, T["P"])
+    np.testing.assert_allclose(rays.cpu().numpy(), o_rays.numpy(), rtol=1e-5, atol=1e-6)
+    assert (o_rays != 0).any()
