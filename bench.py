@@ -61,6 +61,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index, period=0.01):
         super().__init__(daemon=True)
         self.period, self.samples, self.reasons, self.stop_flag = period, [], set(), False
+        self.power_w = []
         self.sm_max = None
         try:
             import pynvml
@@ -82,6 +83,7 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for k, bit in names.items():
                     if r & bit:
@@ -97,7 +99,10 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "sm_mhz_min": float(np.min(self.samples)),
+                "power_w_median": float(np.median(self.power_w)) if self.power_w else None,
+                "power_w_max": float(np.max(self.power_w)) if self.power_w else None}
 
 
 def measured_peak():
@@ -188,11 +193,15 @@ def measured_bf16_peak():
         return 1400.0, "fallback (B200_PROFILING.md)"
 
 
-def convlstm_line(dev):
+def convlstm_line(dev, local=0, steps=12, warmup=4):
     """K2: one ConvLSTM step of workload c3 (C = F = 256, 64^3 voxels, recurrent state present) on the tensor cores.
     Roofline: tensor.  `achieved` counts the f16 MMA work actually issued (3 MMAs per product: the fp32-parity split
     a*2^s = a1 + a2 in fp16 halves, fp32 accumulation); `useful` is the conv's own 2*M*K*N.  Peak = the measured
-    sustained bf16/f16 rate."""
+    sustained bf16/f16 rate.
+
+    Reproducibility: the one-time costs (weight split / transpose, workspace allocation + first touch, first
+    launch) are timed separately; then `warmup` untimed steps, then `steps` steps each bracketed by its own CUDA events, with
+    SM clock / power / throttle reasons sampled DURING the loop.  The headline is the MEDIAN step; min and max are reported."""
     import torch
     import mulit_view_object_detection_b200 as m
     X, C = 64, 256
@@ -201,24 +210,37 @@ def convlstm_line(dev):
     W = torch.randn((3, 3, 3, 2 * C, 4 * C), device=dev, generator=g) * (2.0 / (27 * 2 * C + 4 * C)) ** 0.5
     b = torch.randn(4 * C, device=dev, generator=g) * 0.1
     x = torch.randn((1, X, X, X, C), device=dev, generator=g).relu_()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     cell = m.ConvLSTMTensorCore(W, b, 1.0)
-    h, c = cell.step(x, None, None)
-    for _ in range(2):
+    torch.cuda.synchronize()
+    t_prepare = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    h, c = cell.step(x, None, None)                 # allocates + first-touches the operand workspace, first launch
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - t0
+    for _ in range(warmup):
         cell.step(x, h, c)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 3
-    e0.record()
-    for _ in range(n):
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+    sampler = ClockSampler(local, period=0.005)
+    sampler.start()
+    for k in range(steps):
+        ev[k][0].record()
         h2, c2 = cell.step(x, h, c)
-    e1.record()
+        ev[k][1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
+    clocks = sampler.result()
+    per = sorted(e[0].elapsed_time(e[1]) for e in ev)
+    ms = float(np.median(per))
     flop = 2.0 * X ** 3 * 27 * 2 * C * 4 * C
     peak, src = measured_bf16_peak()
     return {"workload": "c3 step: ConvLSTM 3x3x3, C=F=256, 64^3 voxels, K=13824, N=1024, fp32-parity 3xFP16 split on tcgen05 "
                         "(operand split passes included)",
-            "ms_per_step": ms, "useful_tflops": flop / ms / 1e9,
+            "ms_per_step": ms, "ms_min": per[0], "ms_max": per[-1], "steps": steps, "warmup": warmup,
+            "one_time_ms": {"prepare_weights": t_prepare * 1e3, "first_step_incl_workspace_alloc": t_first * 1e3},
+            "clocks": clocks,
+            "useful_tflops": flop / ms / 1e9,
             "roofline": {"bound": "tensor", "achieved": 3.0 * flop / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
                          "frac": 3.0 * flop / ms / 1e9 / peak, "traffic": None,
                          "peak_source": src, "kernel": "convlstm_tc_kernel<false,true> (K2)"},
@@ -405,7 +427,7 @@ def run_b200(args):
                          "k3_achieved_gbs": k3_bytes / (k3_ms * 1e-3) / 1e9},
         }
         if world == 1 and not args.no_convlstm:
-            line["k2_convlstm"] = convlstm_line(dev)
+            line["k2_convlstm"] = convlstm_line(dev, local)
             line["c2_heads"] = c2_line(dev, peak)
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = 24

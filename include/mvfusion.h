@@ -14,11 +14,12 @@
  *    addresses 16-byte aligned (128-bit vector access); violations return MVF_EALIGN.
  *  - The caller owns every buffer (inputs, outputs, workspaces).  The library never
  *    allocates or frees device memory, never synchronises the stream (except the *_host
- *    entry point, documented there) and keeps no state besides a launch counter and the two
- *    lazily created copy streams of the *_host entry point.
+ *    entry points, documented there) and keeps no state besides a launch counter: the copy
+ *    streams and events of the *_host entry points live in a caller-owned MvfHostAux handle.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *  - Return value: MVF_OK (0) or a negative MVF_E* code; mvf_error_string() describes it.
- *  - Thread-safe and re-entrant per stream.
+ *  - Thread-safe and re-entrant per stream; the *_host entry points are re-entrant per MvfHostAux
+ *    handle (one in-flight call per handle; any number of handles).
  */
 #ifndef MVFUSION_H_
 #define MVFUSION_H_
@@ -44,6 +45,7 @@ extern "C" {
 #define MVF_MAX_SAMPLES   64    /* depth samples per ray                                   */
 #define MVF_MAX_NMS_BOXES 8192  /* candidates per NMS problem                              */
 #define MVF_MAX_CLASSES   256
+#define MVF_WHOLE_GRID    (-1)  /* x_count value meaning "no slab: the whole grid" */
 
 /* Voxel box, the attributes the reference reads from `config`
  * (samples/interior/interior_multi.py:379-386; read at mrcnn/model_multi.py:157-160,267,294-296).
@@ -75,8 +77,9 @@ typedef struct MvfGrid {
  * feats  [B,V,fh,fw,C]        Rcam [B,V,3,4] camera->world        Kmat [B,3,3]
  * Rmain  [B,3,4] or NULL: pose of the MAIN view (reference: Rcam[:,0]); pass it when `Rcam`
  *        holds only a shard of the views (multi-GPU view sharding).
- * x_begin/x_count: compute only the x-slab [x_begin, x_begin+x_count) of the grid
- *        (x_count == 0 -> whole grid); outputs are slab-shaped.
+ * x_begin/x_count: compute only the x-slab [x_begin, x_begin+x_count) of the grid; outputs are slab-shaped.
+ *        x_count == MVF_WHOLE_GRID (any negative value) -> the whole grid.  x_count == 0 is a legitimate EMPTY slab
+ *        (a sharded caller with more ranks than x-planes): nothing is written and MVF_OK is returned.
  * bn_scale/bn_shift [C] or NULL: frozen BatchNorm as x*scale+shift (applied when mode != NONE).
  * out       mode NONE: [B,V,Xs,Y,Z,C]   else [B,Xs,Y,Z,C]
  * out_idx   NULL or int32 [B,V,Xs,Y,Z,2] = (y0,x0) of the bilinear cell (INT32_MIN if unusable)
@@ -204,7 +207,8 @@ int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, const float* 
 
 /* ---- K3: proj_grid ---------------------------------------------------------------------------
  * replaces proj_grid([grid,Rcam,Kmat], config, proj_size)  model_multi.py:231-322 + nearest3 :357-369
- * grid [B,Xs,Y,Z,C] (slab [x_begin, x_begin+x_count) of the full grid; x_count==0 -> whole)
+ * grid [B,Xs,Y,Z,C] (slab [x_begin, x_begin+x_count) of the full grid; x_count < 0 = MVF_WHOLE_GRID -> whole;
+ *      x_count == 0 -> empty slab: `grid` may be NULL and every output sample is 0)
  * Rview [B,3,4]: pose of the camera the rays belong to (reference: Rcam[:,0], :245)
  * Rmain [B,3,4] or NULL (= Rview): pose defining the grid frame (:279-290)
  * grid_pos [B,3] or NULL: required with MVF_FLAG_WORLD_GRID
@@ -245,7 +249,8 @@ int mvf_pyramid_roi_align(const float* boxes, const float* const maps[4], const 
  * replaces tf.image.non_max_suppression as called at model_multi.py:754,1171.
  * nprob independent problems, problem p uses boxes[p*n .. p*n+n).  class_ids NULL or int32
  * [nprob,n]: suppression only between equal classes and at most max_out kept PER CLASS
- * (= the per-class map_fn of :1166-1187); NULL: class-agnostic.
+ * (= the per-class map_fn of :1166-1187); NULL: class-agnostic.  Class ids must lie in [0, MVF_MAX_CLASSES); a box whose
+ * id is outside that range is treated as excluded (never kept, suppresses nothing).
  * keep int32 [nprob,max_total] (indices into the problem's boxes, selection order, -1 padded),
  * keep_count int32 [nprob].  ws: mvf_nms_workspace_bytes(nprob,n) bytes of device scratch. */
 size_t mvf_nms_workspace_bytes(int nprob, int n);
@@ -279,9 +284,15 @@ int mvf_proposals(const float* rpn_probs, const float* rpn_bbox, const float* an
 /* ---- fused pipeline through HOST buffers (the end-to-end entry) -----------------------------
  * unproj_feat -> grid_reas(sum|mean|max [+BN+ReLU]) -> proj_grid for B scenes whose inputs and
  * outputs live in (preferably pinned) HOST memory: copies feats/Rcam/Kmat host->device, runs
- * K1 + K3 and copies the ray slices [B,S,ph,pw,C] back, software-pipelined per scene over two
- * internal streams (ordered after `stream`) so H2D, kernels and D2H overlap, and SYNCHRONISES
- * `stream` before returning.  dev_ws: mvf_pipeline_host_workspace_bytes(...) bytes of device scratch. */
+ * K1 + K3 and copies the ray slices [B,S,ph,pw,C] back, software-pipelined per scene over the three
+ * streams of `aux` (ordered after `stream`) so H2D, kernels and D2H overlap, and SYNCHRONISES
+ * `stream` before returning.  dev_ws: mvf_pipeline_host_workspace_bytes(...) bytes of device scratch.
+ * aux: created once by the caller on the device it will be used on (mvf_host_aux_create: three non-blocking streams and the
+ * events that order them); at most one call may be in flight per handle.  When a call fails after work has been queued,
+ * the handle's streams are drained before the error is returned, so the host buffers are no longer referenced. */
+typedef struct MvfHostAux MvfHostAux;
+int mvf_host_aux_create(MvfHostAux** out);
+int mvf_host_aux_destroy(MvfHostAux* aux);
 size_t mvf_pipeline_host_workspace_bytes(const MvfGrid* g, int B, int V, int fh, int fw, int C,
                                          int proj_h, int proj_w, int samples);
 int mvf_unproject_fuse_project_host(const float* h_feats, const float* h_Rcam, const float* h_Kmat,
@@ -289,7 +300,7 @@ int mvf_unproject_fuse_project_host(const float* h_feats, const float* h_Rcam, c
                                     int img_h, int img_w, int mode, int flags,
                                     const float* d_bn_scale, const float* d_bn_shift,
                                     int proj_h, int proj_w, int samples,
-                                    float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream);
+                                    float* h_out, void* dev_ws, size_t dev_ws_bytes, MvfHostAux* aux, void* stream);
 
 /* One pyramid level of the fusion neck (model_multi.py:2382-2404) from HOST buffers: as above, with depth_sampling (non-conv3d
  * branch, :481-487) fused into the projection, so h_out is PG [B,ph,pw,C] and only features go in / PG comes out.
@@ -301,7 +312,7 @@ int mvf_fusion_neck_level_host(const float* h_feats, const float* h_Rcam, const 
                                const float* d_bn_scale, const float* d_bn_shift,
                                int proj_h, int proj_w, int samples,
                                const float* d_depth_w, float depth_bias, float depth_bn_scale, float depth_bn_shift,
-                               float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream);
+                               float* h_out, void* dev_ws, size_t dev_ws_bytes, MvfHostAux* aux, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 const char* mvf_error_string(int code);

@@ -78,10 +78,12 @@ _SIGS = {
     "mvf_proposals_workspace_bytes": (_sz, [_i, _i, _i]),
     "mvf_proposals": (_i, [_p, _p, _p, C.POINTER(_f), _i, _i, _i, _i, _f, _p, _p, _p, _sz, _p]),
     "mvf_pipeline_host_workspace_bytes": (_sz, [_G, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "mvf_host_aux_create": (_i, [C.POINTER(_p)]),
+    "mvf_host_aux_destroy": (_i, [_p]),
     "mvf_unproject_fuse_project_host": (_i, [_p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p,
-                                             _i, _i, _i, _p, _p, _sz, _p]),
+                                             _i, _i, _i, _p, _p, _sz, _p, _p]),
     "mvf_fusion_neck_level_host": (_i, [_p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p,
-                                        _i, _i, _i, _p, _f, _f, _f, _p, _p, _sz, _p]),
+                                        _i, _i, _i, _p, _f, _f, _f, _p, _p, _sz, _p, _p]),
     "mvf_error_string": (C.c_char_p, [_i]),
     "mvf_version": (C.c_char_p, []),
     "mvf_launch_count": (C.c_ulonglong, []),

@@ -1,6 +1,6 @@
 // Library-level entry points: error strings, launch counter and the HOST-buffer pipeline.
 #include "mvf_common.cuh"
-#include <mutex>
+#include <new>
 
 namespace mvf {
 std::atomic<unsigned long long> g_launches{0};
@@ -49,33 +49,51 @@ extern "C" size_t mvf_pipeline_host_workspace_bytes(const MvfGrid* g, int B, int
     return carve_host(nullptr, g, B, V, fh, fw, C, proj_h, proj_w, samples).bytes;
 }
 
-// Auxiliary streams/events of the host entry point, created lazily once per device (the only
-// library state besides the launch counter): copy-in runs on `sh`, kernels on `sc`, copy-out on `sd`, so
-// the H2D of scene-chunk i+1, the kernels of chunk i and the D2H of chunk i-1 overlap.
+// Auxiliary streams/events of the host entry points live in a caller-owned handle (mvf_host_aux_create): copy-in runs on
+// `sh`, kernels on `sc`, copy-out on `sd`, so the H2D of scene-chunk i+1, the kernels of chunk i and the D2H of chunk i-1
+// overlap.  The library itself keeps no streams, events or per-device state.
 namespace {
 constexpr int kMaxChunks = 32;
-struct Aux { bool ok = false; cudaStream_t sh = nullptr, sc = nullptr, sd = nullptr; cudaEvent_t start = nullptr, done_c = nullptr, done_d = nullptr; cudaEvent_t ev[kMaxChunks] = {}, ev_in[kMaxChunks + 1] = {}; };
-Aux g_aux[64];
-std::mutex g_aux_mu;
-Aux* get_aux() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(g_aux_mu);
-    Aux& a = g_aux[dev];
-    if (!a.ok) {
-        if (cudaStreamCreateWithFlags(&a.sh, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaStreamCreateWithFlags(&a.sc, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaStreamCreateWithFlags(&a.sd, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        cudaEventCreateWithFlags(&a.start, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&a.done_c, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&a.done_d, cudaEventDisableTiming);
-        for (int i = 0; i < kMaxChunks; ++i) cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming);
-        for (int i = 0; i <= kMaxChunks; ++i) cudaEventCreateWithFlags(&a.ev_in[i], cudaEventDisableTiming);
-        a.ok = true;
-    }
-    return &a;
 }
-}  // namespace
+struct MvfHostAux {
+    int device = -1;
+    cudaStream_t sh = nullptr, sc = nullptr, sd = nullptr;
+    cudaEvent_t start = nullptr, done_c = nullptr, done_d = nullptr;
+    cudaEvent_t ev[kMaxChunks] = {}, ev_in[kMaxChunks + 1] = {};
+};
+
+extern "C" int mvf_host_aux_destroy(MvfHostAux* a) {
+    if (!a) return MVF_OK;
+    if (a->sh) { cudaStreamSynchronize(a->sh); cudaStreamDestroy(a->sh); }
+    if (a->sc) { cudaStreamSynchronize(a->sc); cudaStreamDestroy(a->sc); }
+    if (a->sd) { cudaStreamSynchronize(a->sd); cudaStreamDestroy(a->sd); }
+    if (a->start) cudaEventDestroy(a->start);
+    if (a->done_c) cudaEventDestroy(a->done_c);
+    if (a->done_d) cudaEventDestroy(a->done_d);
+    for (int i = 0; i < kMaxChunks; ++i) if (a->ev[i]) cudaEventDestroy(a->ev[i]);
+    for (int i = 0; i <= kMaxChunks; ++i) if (a->ev_in[i]) cudaEventDestroy(a->ev_in[i]);
+    delete a;
+    return MVF_OK;
+}
+
+extern "C" int mvf_host_aux_create(MvfHostAux** out) {
+    if (!out) return MVF_ENULL;
+    *out = nullptr;
+    MvfHostAux* a = new (std::nothrow) MvfHostAux();
+    if (!a) return MVF_EINVAL;
+    bool ok = cudaGetDevice(&a->device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&a->sh, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&a->sc, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&a->sd, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&a->start, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&a->done_c, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&a->done_d, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < kMaxChunks; ++i) ok = cudaEventCreateWithFlags(&a->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i <= kMaxChunks; ++i) ok = cudaEventCreateWithFlags(&a->ev_in[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { mvf_host_aux_destroy(a); return MVF_ECUDA; }       // nothing leaks on a partial creation
+    *out = a;
+    return MVF_OK;
+}
 
 // The reference crosses host->device once per predict() call (mrcnn/model_multi.py:3067-3068);
 // this is the same crossing for the fusion path alone: H2D inputs, K1, K3, D2H ray slices,
@@ -89,20 +107,24 @@ static int host_pipeline(const float* h_feats, const float* h_Rcam, const float*
                          int img_h, int img_w, int mode, int flags,
                          const float* d_bn_scale, const float* d_bn_shift,
                          int proj_h, int proj_w, int samples, const Collapse* col,
-                         float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream) {
-    if (!h_feats || !h_Rcam || !h_Kmat || !g || !h_out || !dev_ws) return MVF_ENULL;
+                         float* h_out, void* dev_ws, size_t dev_ws_bytes, MvfHostAux* ax, void* stream) {
+    if (!h_feats || !h_Rcam || !h_Kmat || !g || !h_out || !dev_ws || !ax) return MVF_ENULL;
     if (B <= 0 || V <= 0 || fh <= 0 || fw <= 0 || C <= 0 || proj_h <= 0 || proj_w <= 0 || samples <= 0) return MVF_EINVAL;
     if (mode < MVF_FUSE_SUM || mode > MVF_FUSE_MAX) return MVF_EINVAL;
     if (!aligned16(dev_ws)) return MVF_EALIGN;
     HostWs w = carve_host(dev_ws, g, B, V, fh, fw, C, proj_h, proj_w, samples);
     if (dev_ws_bytes < w.bytes) return MVF_EWORKSPACE;
-    Aux* ax = get_aux();
-    if (!ax) return MVF_ECUDA;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return MVF_ECUDA;
+    if (dev != ax->device) return MVF_EINVAL;                     // the handle's streams belong to another device
     cudaStream_t s = (cudaStream_t)stream;
     const size_t feat_scene = (size_t)V * fh * fw * C;
     const size_t grid_scene = (size_t)g->nvox * g->nvox * g->nvox_z * C;
     const size_t out_scene = (size_t)(col ? 1 : samples) * proj_h * proj_w * C;      // collapsed: [P,P,C] per scene
-#define MVF_TRY(x) do { if ((x) != cudaSuccess) return MVF_ECUDA; } while (0)
+    // On any failure after work has been queued, drain the three auxiliary streams before returning: the caller owns the
+    // host buffers they read and write, and the next call on this handle must not find stale work in front of it.
+    auto fail = [&](int code) { cudaStreamSynchronize(ax->sh); cudaStreamSynchronize(ax->sc); cudaStreamSynchronize(ax->sd); return code; };
+#define MVF_TRY(x) do { if ((x) != cudaSuccess) return fail(MVF_ECUDA); } while (0)
     // order the auxiliary streams after whatever the caller queued on `stream`
     MVF_TRY(cudaEventRecord(ax->start, s));
     MVF_TRY(cudaStreamWaitEvent(ax->sh, ax->start, 0));
@@ -124,17 +146,17 @@ static int host_pipeline(const float* h_feats, const float* h_Rcam, const float*
         MVF_TRY(cudaEventRecord(ax->ev_in[chunk], ax->sh));
         MVF_TRY(cudaStreamWaitEvent(ax->sc, ax->ev_in[chunk], 0));
         int rc = mvf_unproject_fuse(w.feats + b0 * feat_scene, w.Rcam + (size_t)b0 * V * 12, nullptr, w.Kmat + (size_t)b0 * 9, g,
-                                    nb, V, fh, fw, C, img_h, img_w, mode, flags & ~MVF_FLAG_WORLD_GRID, 0.0, 0, 0,
+                                    nb, V, fh, fw, C, img_h, img_w, mode, flags & ~MVF_FLAG_WORLD_GRID, 0.0, 0, MVF_WHOLE_GRID,
                                     d_bn_scale, d_bn_shift, w.grid + b0 * grid_scene, nullptr, nullptr, nullptr, ax->sc);
-        if (rc != MVF_OK) return rc;
+        if (rc != MVF_OK) return fail(rc);
         if (col)
             rc = mvf_project_depth_collapse(w.grid + b0 * grid_scene, w.R0 + (size_t)b0 * 12, nullptr, w.Kmat + (size_t)b0 * 9, nullptr, g,
-                                            nb, C, img_h, proj_h, proj_w, samples, MVF_FLAG_RELU_OUT, 0.0, 0, 0,
+                                            nb, C, img_h, proj_h, proj_w, samples, MVF_FLAG_RELU_OUT, 0.0, 0, MVF_WHOLE_GRID,
                                             col->d_w, col->bias, col->bn_scale, col->bn_shift, w.out + b0 * out_scene, ax->sc);
         else
             rc = mvf_project_rays(w.grid + b0 * grid_scene, w.R0 + (size_t)b0 * 12, nullptr, w.Kmat + (size_t)b0 * 9, nullptr, g,
-                                  nb, C, img_h, proj_h, proj_w, samples, 0, 0.0, 0, 0, w.out + b0 * out_scene, nullptr, nullptr, ax->sc);
-        if (rc != MVF_OK) return rc;
+                                  nb, C, img_h, proj_h, proj_w, samples, 0, 0.0, 0, MVF_WHOLE_GRID, w.out + b0 * out_scene, nullptr, nullptr, ax->sc);
+        if (rc != MVF_OK) return fail(rc);
         MVF_TRY(cudaEventRecord(ax->ev[chunk], ax->sc));
         MVF_TRY(cudaStreamWaitEvent(ax->sd, ax->ev[chunk], 0));
         MVF_TRY(cudaMemcpyAsync(h_out + b0 * out_scene, w.out + b0 * out_scene, nb * out_scene * sizeof(float),
@@ -154,9 +176,9 @@ extern "C" int mvf_unproject_fuse_project_host(const float* h_feats, const float
                                                int img_h, int img_w, int mode, int flags,
                                                const float* d_bn_scale, const float* d_bn_shift,
                                                int proj_h, int proj_w, int samples,
-                                               float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream) {
+                                               float* h_out, void* dev_ws, size_t dev_ws_bytes, MvfHostAux* aux, void* stream) {
     return host_pipeline(h_feats, h_Rcam, h_Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, d_bn_scale, d_bn_shift,
-                         proj_h, proj_w, samples, nullptr, h_out, dev_ws, dev_ws_bytes, stream);
+                         proj_h, proj_w, samples, nullptr, h_out, dev_ws, dev_ws_bytes, aux, stream);
 }
 
 // One pyramid level of the fusion neck (model_multi.py:2382-2404) from HOST buffers: unproj_feat -> grid_reas(sum|mean|max
@@ -168,9 +190,9 @@ extern "C" int mvf_fusion_neck_level_host(const float* h_feats, const float* h_R
                                           const float* d_bn_scale, const float* d_bn_shift,
                                           int proj_h, int proj_w, int samples,
                                           const float* d_depth_w, float depth_bias, float depth_bn_scale, float depth_bn_shift,
-                                          float* h_out, void* dev_ws, size_t dev_ws_bytes, void* stream) {
+                                          float* h_out, void* dev_ws, size_t dev_ws_bytes, MvfHostAux* aux, void* stream) {
     if (!d_depth_w) return MVF_ENULL;
     const Collapse col = {d_depth_w, depth_bias, depth_bn_scale, depth_bn_shift};
     return host_pipeline(h_feats, h_Rcam, h_Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, d_bn_scale, d_bn_shift,
-                         proj_h, proj_w, samples, &col, h_out, dev_ws, dev_ws_bytes, stream);
+                         proj_h, proj_w, samples, &col, h_out, dev_ws, dev_ws_bytes, aux, stream);
 }

@@ -632,7 +632,9 @@ static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 // Operand format of the k=3 convolutions: fp16 halves (twice the MMA rate) whenever every source has a multiple of 64 channels.
 // MVF_TC_TF32=1 forces the tf32 split everywhere (A/B measurement); the fused in-kernel converter is tf32 only.
-static bool env_flag(const char* name) { const char* e = getenv(name); return e && atoi(e) != 0; }
+static bool env_flag(const char* name) { return env_int(name, 0) != 0; }
+// ONE predicate decides the fp16 weight / activation format, at prepare time and at call time alike (the debug switches are
+// read once, together; in the product build they do not exist).
 static bool want_f16(int C, int C2) {
     static const bool off = env_flag("MVF_TC_TF32") || env_flag("MVF_TC_FUSED_SPLIT");
     return !off && C % TC_K16 == 0 && C2 % TC_K16 == 0;
@@ -691,7 +693,7 @@ extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, co
     // The hi/lo halves of x and h are produced by a separate elementwise pass: every element is read 27 x 4F/256 times by the
     // GEMM, so the pass costs 1 % while converting inside the 2-stage ring costs 10 % (measured: 35.7 vs 32.3 ms at c3 size).
     // MVF_TC_FUSED_SPLIT=1 selects the in-kernel converter for A/B measurement.
-    static const bool split_pass = [] { const char* e = getenv("MVF_TC_FUSED_SPLIT"); return !(e && atoi(e) != 0); }();
+    static const bool split_pass = !env_flag("MVF_TC_FUSED_SPLIT");
     if (split_pass && (!ws || ws_bytes < mvf_convlstm_tc_workspace_bytes(B, Xin, Y, Z, C, F))) return MVF_EWORKSPACE;
     if (!encode_tiled()) return MVF_ECUDA;
     cudaStream_t s = (cudaStream_t)stream;
@@ -743,7 +745,7 @@ extern "C" int mvf_convlstm_step_tc_slab(const float* x, const float* h_prev, co
     a.fused_split = !split_pass; a.relu_x = relu_in; a.relu_h = 0; a.pre_scale = nullptr; a.pre_shift = nullptr;
     a.V = 1; a.Cout = 0; a.kind = 0; a.ksize = 3; a.relu_out = 0; a.bn_scale = nullptr; a.bn_shift = nullptr; a.out = nullptr;
     // K-chunks (of 32) per partial accumulation chain; MVF_TC_PROMOTE overrides (0 = one long chain, for A/B measurement)
-    static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
+    static const int promote_env = env_int("MVF_TC_PROMOTE", -1);
     a.promote = promote_env >= 0 ? promote_env : 8;
     const int K = 27 * (C + F);
     const long long wtotal = (long long)K * 4 * F;
@@ -789,7 +791,7 @@ extern "C" size_t mvf_conv3d_wsplit_bytes(int kind, int ksize, int Cin, int Cout
 }
 
 static bool conv3d_f16(int ksize, int C, int C2, bool pre_affine) { return ksize == 3 && !pre_affine && want_f16(C, C2); }
-static bool conv3d_f16_presplit(int C, int C2) { return C % TC_K16 == 0 && C2 % TC_K16 == 0 && !env_flag("MVF_TC_TF32"); }
+static bool conv3d_f16_presplit(int C, int C2) { return want_f16(C, C2); }
 
 extern "C" int mvf_conv3d_prepare(const float* W, int kind, int ksize, int V, int C, int C2, int Cout, int chan_interleave,
                                   float* wsplit, void* stream) {
@@ -835,10 +837,7 @@ extern "C" int mvf_conv3d_prepare(const float* W, int kind, int ksize, int V, in
 // inside the GEMM (warps 2-3) and touch no workspace: 'ident' 2048->256 at 64^3 1.67 ms instead of 2.60.
 // MVF_TC_SPLIT_PASS=1 / MVF_TC_FUSED_SPLIT=1 force either choice (the stride-2 conv always needs the pass: it re-lays the operand).
 static bool conv3d_fused_split(int kind, int ksize, int B, int X, int Y, int Z, int Cout) {
-    static const int force = [] {
-        const char* p = getenv("MVF_TC_SPLIT_PASS"); const char* f = getenv("MVF_TC_FUSED_SPLIT");
-        return (p && atoi(p) != 0) ? 1 : (f && atoi(f) != 0) ? 2 : 0;
-    }();
+    static const int force = env_flag("MVF_TC_SPLIT_PASS") ? 1 : env_flag("MVF_TC_FUSED_SPLIT") ? 2 : 0;
     if (kind == MVF_CONV_S2 || force == 1) return false;
     if (force == 2) return true;
     const long long tiles = (((long long)B * X * Y * Z + TC_M - 1) / TC_M) * ((Cout + TC_N - 1) / TC_N);
@@ -935,7 +934,7 @@ extern "C" int mvf_conv3d_tc(const float* in, const float* in2, const float* wsp
     a.fused_split = !split_pass; a.relu_x = relu_in; a.relu_h = relu_in; a.pre_scale = pre_scale; a.pre_shift = pre_shift;
     a.V = V; a.Cout = Cout; a.kind = kind; a.ksize = ksize; a.relu_out = (flags & MVF_FLAG_RELU_OUT) != 0;
     a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.out = out;
-    static const int promote_env = [] { const char* e = getenv("MVF_TC_PROMOTE"); return e ? atoi(e) : -1; }();
+    static const int promote_env = env_int("MVF_TC_PROMOTE", -1);
     a.promote = promote_env >= 0 ? promote_env : 8;
     const int K = conv_taps(kind, ksize) * (V * C + C2);
     const long long wtotal = (long long)K * Cout;

@@ -124,11 +124,15 @@ __device__ __forceinline__ bool iou_above(const float4 a, const float4 b, float 
 }
 
 // ---- NMS stages --------------------------------------------------------------------------------
-__global__ void nms_keys_kernel(const float* scores, u64* keys, int n, int n_pad) {
+// A class id outside [0, MVF_MAX_CLASSES) would index the scan's shared per-class counters out of bounds: such a box gets the
+// EXCLUDED key here, so it sorts behind every candidate (never kept, suppresses nothing) -- the documented contract of mvf_nms.
+__global__ void nms_keys_kernel(const float* scores, const int32_t* class_ids, u64* keys, int n, int n_pad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int pb = blockIdx.y;
     if (i >= n_pad) return;
-    keys[(size_t)pb * n_pad + i] = (i < n) ? make_key(scores[(size_t)pb * n + i], (unsigned)i) : KEY_EXCLUDED;
+    bool ok = i < n;
+    if (ok && class_ids) { const int c = class_ids[(size_t)pb * n + i]; ok = c >= 0 && c < MVF_MAX_CLASSES; }
+    keys[(size_t)pb * n_pad + i] = ok ? make_key(scores[(size_t)pb * n + i], (unsigned)i) : KEY_EXCLUDED;
 }
 
 // sorted position r -> (original index | -1, box, class)
@@ -403,7 +407,7 @@ extern "C" int mvf_nms(const float* boxes, const float* scores, const int32_t* c
     if (ws_bytes < w.bytes) return MVF_EWORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 gk((n_pad + 255) / 256, nprob);
-    nms_keys_kernel<<<gk, 256, 0, s>>>(scores, w.keys, n, n_pad);
+    nms_keys_kernel<<<gk, 256, 0, s>>>(scores, class_ids, w.keys, n, n_pad);
     count_launch();
     int rc = sort_keys(w.keys, nprob, n_pad, s);
     if (rc != MVF_OK) return rc;

@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdlib.h>
 #include <atomic>
 #include "mvfusion.h"
 
@@ -19,6 +20,14 @@ inline int check_launch() {
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// A/B measurement switches (MVF_K1_*, MVF_TC_*) exist only in builds made with -DMVF_DEBUG_ENV (make DEBUG_ENV=1): the product
+// library reads no environment variables, so an operand format or kernel variant is a pure function of the call's arguments.
+#ifdef MVF_DEBUG_ENV
+inline int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+inline int env_int(const char*, int dflt) { return dflt; }
+#endif
 
 // ---- pinned fp32 arithmetic: every op individually rounded, no FMA contraction --------------
 // (dot products left-to-right in ascending k).

@@ -198,13 +198,14 @@ depth_collapse_kernel(const float* __restrict__ in, const float* __restrict__ w,
 static int fill_proj_params(ProjParams& p, const float* grid, const float* Rview, const float* Rmain, const float* Kmat,
                             const float* grid_pos, const MvfGrid* g, int B, int C, int img_h, int proj_h, int proj_w,
                             int samples, int flags, double grid_dist, int x_begin, int x_count) {
-    if (!grid || !Rview || !Kmat || !g) return MVF_ENULL;
+    if (!Rview || !Kmat || !g) return MVF_ENULL;
+    if (!grid && x_count != 0) return MVF_ENULL;                          // an empty slab has no grid memory
     if (B <= 0 || C <= 0 || img_h <= 0 || proj_h <= 0 || proj_w <= 0 || samples <= 0) return MVF_EINVAL;
-    if (C % 4 != 0 || !aligned16(grid)) return MVF_EALIGN;
+    if (C % 4 != 0 || (grid && !aligned16(grid))) return MVF_EALIGN;
     if (samples > MVF_MAX_SAMPLES || g->nvox > MVF_MAX_DIM || g->nvox_z > MVF_MAX_DIM || B > 65535 || C > 1024) return MVF_EUNSUPPORTED;
     if ((flags & MVF_FLAG_WORLD_GRID) && !grid_pos) return MVF_ENULL;
-    if (x_count == 0) { x_begin = 0; x_count = g->nvox; }
-    if (x_begin < 0 || x_count < 0 || x_begin + x_count > g->nvox) return MVF_EINVAL;
+    if (x_count < 0) { x_begin = 0; x_count = g->nvox; }                  // MVF_WHOLE_GRID; x_count == 0: every sample misses the slab
+    if (x_begin < 0 || x_begin + x_count > g->nvox) return MVF_EINVAL;
     p.grid = grid; p.Rview = Rview; p.Rmain = Rmain; p.Kmat = Kmat;
     p.grid_pos = (flags & MVF_FLAG_WORLD_GRID) ? grid_pos : nullptr;
     p.w = nullptr; p.out = nullptr; p.out_vox = nullptr; p.out_valid = nullptr;

@@ -418,7 +418,7 @@ static int launch_run(const UnprojParams& p, int B, cudaStream_t s) {
     const long long cols = (long long)((p.Xs + RUN_TX - 1) / RUN_TX) * ((p.Y + RUN_TY - 1) / RUN_TY);
     // a CTA walks tiles_z / zsplit z-tiles of its 4x2 columns; split z only as far as needed to give every
     // SM several CTAs (2 resident per SM, >= 4 waves)
-    static const int zs_env = [] { const char* e = getenv("MVF_K1_ZSPLIT"); return e ? atoi(e) : 0; }();
+    static const int zs_env = env_int("MVF_K1_ZSPLIT", 0);
     int zsplit = 1;
     while (zsplit < tiles_z && cols * zsplit * B * nchunk < 148ll * 2 * 4) zsplit *= 2;
     if (zs_env > 0) zsplit = zs_env;
@@ -459,7 +459,7 @@ static int unproject_impl(const float* feats, const float* Rcam, const float* Rm
                           const float* bn_scale, const float* bn_shift,
                           float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
                           uint2* out16_hi, uint2* out16_lo, unsigned* split_tail, int out16_s2d, void* stream) {
-    if (!feats || !Rcam || !Kmat || !g || (!out && !out16_hi)) return MVF_ENULL;
+    if (!feats || !Rcam || !Kmat || !g) return MVF_ENULL;
     if (B <= 0 || V <= 0 || fh <= 0 || fw <= 0 || C <= 0 || img_h <= 0 || img_w <= 0) return MVF_EINVAL;
     if (mode < MVF_FUSE_NONE || mode > MVF_FUSE_MAX) return MVF_EINVAL;
     if ((bn_scale == nullptr) != (bn_shift == nullptr)) return MVF_ENULL;
@@ -470,8 +470,10 @@ static int unproject_impl(const float* feats, const float* Rcam, const float* Rm
     UnprojParams p;
     int rc = fill_centres(g, flags, p.gx, p.gy, p.gz);
     if (rc != MVF_OK) return rc;
-    if (x_count == 0) { x_begin = 0; x_count = g->nvox; }
-    if (x_begin < 0 || x_count < 0 || x_begin + x_count > g->nvox) return MVF_EINVAL;
+    if (x_count < 0) { x_begin = 0; x_count = g->nvox; }                   // MVF_WHOLE_GRID
+    if (x_begin < 0 || x_begin + x_count > g->nvox) return MVF_EINVAL;
+    if (x_count == 0) return MVF_OK;                                        // empty slab of a sharded caller: nothing to write
+    if (!out && !out16_hi) return MVF_ENULL;
     p.feats = feats; p.Rcam = Rcam; p.Rmain = Rmain; p.Kmat = Kmat;
     p.bn_scale = (mode == MVF_FUSE_NONE) ? nullptr : bn_scale;
     p.bn_shift = (mode == MVF_FUSE_NONE) ? nullptr : bn_shift;
@@ -489,7 +491,7 @@ static int unproject_impl(const float* feats, const float* Rcam, const float* Rm
     // One warp covers 256 channels x 8 z-steps when C is a multiple of 256 (the FPN width), else
     // 128 channels x 16 z-steps.  MVF_K1_VARIANT (debug / A-B measurement) overrides:
     // 1 = 128ch x 16, 2 = 256ch x 8, 3 = 128ch x 8.
-    static const int variant = [] { const char* e = getenv("MVF_K1_VARIANT"); return e ? atoi(e) : -1; }();
+    static const int variant = env_int("MVF_K1_VARIANT", -1);
     if (variant == 1) return launch_run<1, 16>(p, B, s);
     if (variant == 2) return launch_run<2, 8>(p, B, s);
     if (variant == 3) return launch_run<1, 8>(p, B, s);
@@ -502,7 +504,7 @@ extern "C" int mvf_unproject_fuse(const float* feats, const float* Rcam, const f
                                   const float* bn_scale, const float* bn_shift,
                                   float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
                                   void* stream) {
-    if (!out) return MVF_ENULL;
+    if (!out && x_count != 0) return MVF_ENULL;
     return unproject_impl(feats, Rcam, Rmain, Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, grid_dist, x_begin, x_count,
                           bn_scale, bn_shift, out, out_idx, out_valid, out_grid_pos, nullptr, nullptr, nullptr, 0, stream);
 }
@@ -524,6 +526,6 @@ extern "C" int mvf_unproject_split_f16(const float* feats, const float* Rcam, co
     __half* w0 = (__half*)conv_ws;
     unsigned* tail = (unsigned*)(((uintptr_t)(w0 + 2 * n1) + 15) & ~(uintptr_t)15);
     if (cudaMemcpyAsync(tail, act_amax, 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) return MVF_ECUDA;
-    return unproject_impl(feats, Rcam, Rmain, Kmat, g, B, V, fh, fw, C, img_h, img_w, MVF_FUSE_NONE, flags & MVF_FLAG_RELU_IN, 0.0, 0, 0,
+    return unproject_impl(feats, Rcam, Rmain, Kmat, g, B, V, fh, fw, C, img_h, img_w, MVF_FUSE_NONE, flags & MVF_FLAG_RELU_IN, 0.0, 0, MVF_WHOLE_GRID,
                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (uint2*)w0, (uint2*)(w0 + n1), tail, sublattices != 0, stream);
 }

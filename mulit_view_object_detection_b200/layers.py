@@ -942,6 +942,16 @@ class HostPipeline:
         self.bn = _bn_affine(bn, Cc, device)
         self.flags = _lib.FLAG_RELU_OUT if relu_out else 0
         self.d2h_bytes = 4 * B * (1 if self.depth else self.S) * self.ph * self.pw * Cc
+        # the three copy / compute streams and their events: owned by this object, created on `device` (mvf_host_aux_create)
+        self.aux = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib.mvf_host_aux_create(C.byref(self.aux)), "mvf_host_aux_create")
+
+    def __del__(self):
+        aux = getattr(self, "aux", None)
+        if aux:
+            lib.mvf_host_aux_destroy(aux)
+            self.aux = None
 
     def empty_output(self):
         B, _, _, _, Cc = self.shape
@@ -961,11 +971,11 @@ class HostPipeline:
             rc = lib.mvf_fusion_neck_level_host(_ptr(h_feats), _ptr(h_Rcam), _ptr(h_Kmat), C.byref(self.g), B, V, fh, fw, Cc,
                                                 ih, iw, self.mode, self.flags, _ptr(self.bn[0]), _ptr(self.bn[1]),
                                                 self.ph, self.pw, self.S, _ptr(w), bias, inv, shift,
-                                                _ptr(h_out), _ptr(self.ws), self.nbytes, _stream())
+                                                _ptr(h_out), _ptr(self.ws), self.nbytes, self.aux, _stream())
             check(rc, "mvf_fusion_neck_level_host")
             return h_out
         rc = lib.mvf_unproject_fuse_project_host(_ptr(h_feats), _ptr(h_Rcam), _ptr(h_Kmat), C.byref(self.g), B, V, fh, fw, Cc,
                                                  ih, iw, self.mode, self.flags, _ptr(self.bn[0]), _ptr(self.bn[1]),
-                                                 self.ph, self.pw, self.S, _ptr(h_out), _ptr(self.ws), self.nbytes, _stream())
+                                                 self.ph, self.pw, self.S, _ptr(h_out), _ptr(self.ws), self.nbytes, self.aux, _stream())
         check(rc, "mvf_unproject_fuse_project_host")
         return h_out
