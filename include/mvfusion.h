@@ -92,6 +92,21 @@ int mvf_unproject_fuse(const float* feats, const float* Rcam, const float* Rmain
                        float* out, int32_t* out_idx, uint8_t* out_valid, float* out_grid_pos,
                        void* stream);
 
+/* ---- K1T: the same fused unproject + view reduction on the tensor cores (tcgen05) ----------------------------------------
+ * Same arguments and results as mvf_unproject_fuse (features within the fp32 tolerance) for the LINEAR view
+ * reductions: mode MVF_FUSE_SUM | MVF_FUSE_MEAN, no MVF_FLAG_RELU_IN, C % 64 == 0, 64 <= C <= 256; no index / mask side
+ * outputs.  mvf_unproject_fuse_tc_supported() tells whether a configuration qualifies (else MVF_EUNSUPPORTED: use
+ * mvf_unproject_fuse).  ws: mvf_unproject_fuse_tc_workspace_bytes(...) bytes of device scratch (the fp16 operand halves of the
+ * features).  Bilinear sampling of a 4x4x8 voxel tile is evaluated as out[128, C] += W_v[128, K] . F_v[K, C] per view with
+ * the accumulators in TMEM; voxel->pixel coordinates and weights are computed exactly as in mvf_unproject_fuse. */
+int mvf_unproject_fuse_tc_supported(int V, int C, int mode, int flags);
+size_t mvf_unproject_fuse_tc_workspace_bytes(int B, int V, int fh, int fw, int C);
+int mvf_unproject_fuse_tc(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat,
+                          const MvfGrid* g, int B, int V, int fh, int fw, int C, int img_h, int img_w,
+                          int mode, int flags, double grid_dist, int x_begin, int x_count,
+                          const float* bn_scale, const float* bn_shift, float* out,
+                          void* ws, size_t ws_bytes, void* stream);
+
 /* unproj_feat written straight into the operand format of the convolution that consumes it -- the 'conv3d' U-Net's first
  * convolution (model_multi.py:411-421; sublattices = 1: parity-sub-lattice layout of MVF_CONV_S2) or the 'ident' 1x1x1 conv
  * (:446-453; sublattices = 0) -- as fp16 (hi, lo) halves, into the workspace a following

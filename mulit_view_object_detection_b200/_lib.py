@@ -47,6 +47,10 @@ _G = C.POINTER(MvfGrid)
 _SIGS = {
     "mvf_unproject_fuse": (_i, [_p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i,
                                 _p, _p, _p, _p, _p, _p, _p]),
+    "mvf_unproject_fuse_tc_supported": (_i, [_i, _i, _i, _i]),
+    "mvf_unproject_fuse_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "mvf_unproject_fuse_tc": (_i, [_p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _d, _i, _i,
+                                   _p, _p, _p, _p, _sz, _p]),
     "mvf_unproject_split_f16": (_i, [_p, _p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "mvf_view_reduce": (_i, [_p, _i, _i, _ll, _i, _i, _i, _p, _p, _p, _p]),
     "mvf_channel_mean": (_i, [_p, _i, _i, _ll, _i, _p, _p]),

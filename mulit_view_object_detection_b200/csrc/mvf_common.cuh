@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <atomic>
 #include "mvfusion.h"
 
@@ -16,6 +17,9 @@ inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_o
 
 inline int check_launch() {
     cudaError_t e = cudaGetLastError();
+#ifdef MVF_DEBUG_ENV
+    if (e != cudaSuccess) fprintf(stderr, "libmvfusion: launch failed: %s\n", cudaGetErrorString(e));
+#endif
     return e == cudaSuccess ? MVF_OK : MVF_ECUDA;
 }
 

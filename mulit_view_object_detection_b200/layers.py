@@ -126,9 +126,24 @@ _FUSE = {"none": _lib.FUSE_NONE, "sum": _lib.FUSE_SUM, "add": _lib.FUSE_SUM, "me
 
 
 # ------------------------------------------------------------------------------------------------
+_k1t_ws = {}          # device -> scratch of the tensor-core path (fp16 operand halves of the features), grown on demand
+
+
+def _k1t_workspace(device, nbytes):
+    ws = _k1t_ws.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        _k1t_ws[device] = ws
+    return ws
+
+
 def unproject_fuse(feats, Rcam, Kmat, config, mode="sum", bn=None, relu_in=False, relu_out=False,
-                   Rmain=None, x_slab=None, world_grid=False, return_aux=False, out=None):
-    """K1: unproject every view and reduce over views in registers.
+                   Rmain=None, x_slab=None, world_grid=False, return_aux=False, out=None, tensor_cores=None):
+    """K1: unproject every view and reduce over views on chip (the per-view grids never exist).
+
+    ``tensor_cores``: None = automatic -- the linear reductions (sum / mean, no ReLU in front, C % 64 == 0, C <= 256, no side
+    outputs) run as K1T on tcgen05 (``mvf_unproject_fuse_tc``), everything else on the CUDA-core slot kernel
+    (``mvf_unproject_fuse``); True / False force either (True raises when the configuration does not qualify).
 
     mode 'none' -> [B,V,Xs,Y,Z,C] (= unproj_feat), else [B,Xs,Y,Z,C].
     ``Rmain`` [B,3,4]: main-view pose when ``Rcam`` is a shard of the views.
@@ -166,6 +181,19 @@ def unproject_fuse(feats, Rcam, Kmat, config, mode="sum", bn=None, relu_in=False
             (_lib.FLAG_WORLD_GRID if world_grid else 0)
     grid_dist = float(getattr(config, "GRID_DIST", 600 / 320 * config.vmax))
     ih, iw = _image_hw(config)
+    if xc == 0:                       # empty slab of a sharded caller: nothing to compute
+        tensor_cores = False
+    eligible = bool(lib.mvf_unproject_fuse_tc_supported(V, Cc, m, flags)) and not return_aux and not world_grid
+    if tensor_cores and not eligible:
+        raise ValueError("the tensor-core unprojection needs mode sum/mean, no relu_in, C % 64 == 0, C <= 256 and no side outputs")
+    if eligible and tensor_cores is not False:
+        nbytes = lib.mvf_unproject_fuse_tc_workspace_bytes(B, V, fh, fw, Cc)
+        ws = _k1t_workspace(feats.device, nbytes)
+        rc = lib.mvf_unproject_fuse_tc(_ptr(feats), _ptr(Rcam), _ptr(Rmain), _ptr(Kmat), C.byref(g), B, V, fh, fw, Cc,
+                                       ih, iw, m, flags, grid_dist, xb, xc, _ptr(scale), _ptr(shift), _ptr(out),
+                                       _ptr(ws), ws.numel(), _stream())
+        check(rc, "mvf_unproject_fuse_tc")
+        return out
     rc = lib.mvf_unproject_fuse(_ptr(feats), _ptr(Rcam), _ptr(Rmain), _ptr(Kmat), C.byref(g), B, V, fh, fw, Cc,
                                 ih, iw, m, flags, grid_dist, xb, xc, _ptr(scale), _ptr(shift),
                                 _ptr(out), _ptr(idx), _ptr(valid), _ptr(gpos), _stream())
@@ -660,10 +688,10 @@ def proj_grid_depth_sampling(inputs, config, proj_size, name, params=None, view=
 
 
 def unproject_fuse_project(feats, Rcam, Kmat, config, proj_size, mode="sum", bn=None, relu_out=False,
-                           grid_out=None, out=None):
+                           grid_out=None, out=None, tensor_cores=None):
     """The fused pipeline: unproj_feat -> grid_reas(sum|mean|max [+BN+ReLU]) -> proj_grid.
-    Two launches (K1, K3); returns (ray slices [B,S,P,P,C], fused grid [B,X,Y,Z,C])."""
-    fused = unproject_fuse(feats, Rcam, Kmat, config, mode=mode, bn=bn, relu_out=relu_out, out=grid_out)
+    Two launches (K1 or K1T, K3); returns (ray slices [B,S,P,P,C], fused grid [B,X,Y,Z,C])."""
+    fused = unproject_fuse(feats, Rcam, Kmat, config, mode=mode, bn=bn, relu_out=relu_out, out=grid_out, tensor_cores=tensor_cores)
     rays = proj_grid([fused, Rcam, Kmat], config, proj_size, out=out)
     return rays, fused
 
