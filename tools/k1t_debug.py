@@ -56,9 +56,35 @@ def timing():
               (tc, ms, B, ms * 1e3 / B, (1024.0 * (12800 + 262144) * B / (ms * 1e-3) / 1e9) / 6560.0), flush=True)
 
 
+def prof():
+    """Per-role cycle counters of CTA 0 (DEBUG_ENV build)."""
+    import ctypes
+    import torch
+    import mulit_view_object_detection_b200 as m
+    from mulit_view_object_detection_b200 import synthetic as syn, _lib
+    cfg = m.FusionConfig(nvox=64, nvox_z=64, samples=20, NUM_VIEWS=8)
+    B = 16
+    feats, Rcam, Kmat = syn.make_scene(cfg, B, 8, 40, 40, 256, seed=1000)
+    d = [torch.from_numpy(a).cuda() for a in (feats, Rcam, Kmat)]
+    grid = torch.empty((B, 64, 64, 64, 256), device="cuda")
+    for _ in range(3):
+        m.unproject_fuse(*d, cfg, mode="sum", out=grid, tensor_cores=True)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_ulonglong * 32)()
+    _lib.lib.mvf_debug_k1t_prof.restype = ctypes.c_int
+    assert _lib.lib.mvf_debug_k1t_prof(buf) == 0
+    v = list(buf)
+    names = {0: "compute half0 [total, phaseA+bbox, empty-wait, produce, header, ksteps]", 8: "compute half1", 16: "MMA [total, full-wait, acc_empty-wait, ksteps, header-wait]",
+             24: "epilogue [total, acc_full-wait, staging-wait, work]"}
+    for base, nm in names.items():
+        print("%-70s %s" % (nm, v[base:base + 8]))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child(int(sys.argv[2]))
+    elif len(sys.argv) > 1 and sys.argv[1] == "prof":
+        prof()
     elif len(sys.argv) > 1 and sys.argv[1] == "timing":
         timing()
     else:
