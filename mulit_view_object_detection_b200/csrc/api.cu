@@ -27,7 +27,7 @@ extern "C" const char* mvf_version(void) { return "mvfusion 0.1.0 (sm_100a)"; }
 extern "C" unsigned long long mvf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // device scratch layout of the host pipeline: feats | Rcam | Kmat | fused grid | ray slices
-struct HostWs { float *feats, *Rcam, *R0, *Kmat, *grid, *out; size_t bytes; };
+struct HostWs { float *feats, *Rcam, *R0, *Kmat, *grid, *out; char* k1t; size_t k1t_scene, bytes; };
 
 static HostWs carve_host(void* ws, const MvfGrid* g, int B, int V, int fh, int fw, int C, int ph, int pw, int S) {
     HostWs w;
@@ -39,6 +39,9 @@ static HostWs carve_host(void* ws, const MvfGrid* g, int B, int V, int fh, int f
     w.Kmat = (float*)(p + off); off += align_up256((size_t)B * 9 * sizeof(float));
     w.grid = (float*)(p + off); off += align_up256((size_t)B * g->nvox * g->nvox * g->nvox_z * C * sizeof(float));
     w.out = (float*)(p + off); off += align_up256((size_t)B * S * ph * pw * C * sizeof(float));
+    // scratch of the tensor-core unprojection (fp16 operand halves of one scene's features), one region per scene
+    w.k1t_scene = align_up256(mvf_unproject_fuse_tc_workspace_bytes(1, V, fh, fw, C));
+    w.k1t = p + off; off += (size_t)B * w.k1t_scene;
     w.bytes = off;
     return w;
 }
@@ -145,7 +148,16 @@ static int host_pipeline(const float* h_feats, const float* h_Rcam, const float*
                                 cudaMemcpyHostToDevice, ax->sh));
         MVF_TRY(cudaEventRecord(ax->ev_in[chunk], ax->sh));
         MVF_TRY(cudaStreamWaitEvent(ax->sc, ax->ev_in[chunk], 0));
-        int rc = mvf_unproject_fuse(w.feats + b0 * feat_scene, w.Rcam + (size_t)b0 * V * 12, nullptr, w.Kmat + (size_t)b0 * 9, g,
+        // K1T (tensor cores) for the linear reductions it supports, else the CUDA-core slot kernel -- the same choice the
+        // Python mirror makes, so both entries return the same bits
+        int rc;
+        if (mvf_unproject_fuse_tc_supported(V, C, mode, flags & ~MVF_FLAG_WORLD_GRID))
+            rc = mvf_unproject_fuse_tc(w.feats + b0 * feat_scene, w.Rcam + (size_t)b0 * V * 12, nullptr, w.Kmat + (size_t)b0 * 9, g,
+                                       nb, V, fh, fw, C, img_h, img_w, mode, flags & ~MVF_FLAG_WORLD_GRID, 0.0, 0, MVF_WHOLE_GRID,
+                                       d_bn_scale, d_bn_shift, w.grid + b0 * grid_scene, w.k1t + (size_t)b0 * w.k1t_scene,
+                                       (size_t)nb * w.k1t_scene, ax->sc);
+        else
+            rc = mvf_unproject_fuse(w.feats + b0 * feat_scene, w.Rcam + (size_t)b0 * V * 12, nullptr, w.Kmat + (size_t)b0 * 9, g,
                                     nb, V, fh, fw, C, img_h, img_w, mode, flags & ~MVF_FLAG_WORLD_GRID, 0.0, 0, MVF_WHOLE_GRID,
                                     d_bn_scale, d_bn_shift, w.grid + b0 * grid_scene, nullptr, nullptr, nullptr, ax->sc);
         if (rc != MVF_OK) return fail(rc);

@@ -48,7 +48,10 @@ struct UnprojParams {
 //           the per-slot "reload" flags, individually rounded fp32 (bit-exact vs the oracle),
 //           written to a 32-slot per-warp shared-memory table; masks travel as ballots;
 //   phase B (lanes = float4 channel slots): walk the run.
-constexpr int RUN_WARPS = 8, RUN_TX = 4, RUN_TY = 2;
+#ifndef MVF_K1_TX
+#define MVF_K1_TX 4
+#endif
+constexpr int RUN_TX = MVF_K1_TX, RUN_TY = 2, RUN_WARPS = RUN_TX * RUN_TY;
 
 template <int CPL, int L, int MODE, bool RELU_IN, bool FULLC, bool AUX>
 __global__ void __launch_bounds__(RUN_WARPS * 32, (CPL * L <= 16) ? 2 : 1)

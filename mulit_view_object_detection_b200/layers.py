@@ -184,6 +184,11 @@ def unproject_fuse(feats, Rcam, Kmat, config, mode="sum", bn=None, relu_in=False
     if xc == 0:                       # empty slab of a sharded caller: nothing to compute
         tensor_cores = False
     eligible = bool(lib.mvf_unproject_fuse_tc_supported(V, Cc, m, flags)) and not return_aux and not world_grid
+    if tensor_cores is None and x_slab is not None and (xb % 4 != 0 or (xc % 4 != 0 and xb + xc != g.nvox)):
+        # K1T works on 4x4x8 voxel tiles anchored at the slab origin; a slab that cuts the full grid's tiles would see other
+        # per-tile footprints and K orders, i.e. last-bit differences from the unsharded result.  Such slabs (the 1-voxel halo
+        # slabs of dist.lstm_slab) stay on the slot kernel, whose per-voxel arithmetic is independent of the slab.
+        eligible = False
     if tensor_cores and not eligible:
         raise ValueError("the tensor-core unprojection needs mode sum/mean, no relu_in, C % 64 == 0, C <= 256 and no side outputs")
     if eligible and tensor_cores is not False:
