@@ -114,12 +114,14 @@ def measured_peak():
 
 
 def k1_traffic_bytes(B):
-    """dram bytes per K1 launch from the committed ncu capture (profiles/k1_traffic.json), scaled to B scenes."""
+    """DRAM bytes per K1 launch, STATIC: taken from the committed `ncu --set full` capture of the same kernel on the same workload
+    (profiles/k1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per scene) and scaled to B scenes -- not measured in
+    this run (ncu cannot run inside the timed bench)."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
-        return float(d["dram_bytes_per_scene"]) * B
+        return float(d["dram_bytes_per_scene"]) * B, "static: %s" % d.get("source", "profiles/k1_traffic.json")
     except Exception:
-        return None
+        return None, None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -349,6 +351,16 @@ def run_b200(args):
     barrier()
     launches = m.launch_count() - n0
     clocks = sampler.result()
+    # the CUDA-core slot kernel on the same inputs, for the record (not part of the timed step)
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m.unproject_fuse(d_feats, d_R, d_K, cfg, mode="sum", out=grid, tensor_cores=False)
+    es0.record(stream)
+    for _ in range(3):
+        m.unproject_fuse(d_feats, d_R, d_K, cfg, mode="sum", out=grid, tensor_cores=False)
+    es1.record(stream)
+    torch.cuda.synchronize()
+    k1_slot_ms = es0.elapsed_time(es1) / 3
+    m.unproject_fuse(d_feats, d_R, d_K, cfg, mode="sum", out=grid)            # leave the K1T result in `grid`
     total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
     k1_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
     k3_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
@@ -404,6 +416,7 @@ def run_b200(args):
         peak, peak_src = measured_peak()
         k1_bytes, k3_bytes = algorithmic_bytes(B)
         achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+        traffic, traffic_src = k1_traffic_bytes(B)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -417,10 +430,14 @@ def run_b200(args):
                                              "+ K3b + D2H + sync) -- the host/device boundary of the reference model; extra to `e2e`",
                          "checksum": neck_checksum},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "unproject_slot_kernel (K1)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": k1_traffic_bytes(B), "peak_source": peak_src,
+            "roofline": {"kernel": "unproject_tc_kernel (K1T: tcgen05 unprojection; the time includes its two feature-split passes)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms,
-                         "share_of_step": k1_ms / (k1_ms + k3_ms)},
+                         "share_of_step": k1_ms / (k1_ms + k3_ms),
+                         "cuda_core_slot_kernel_ms": k1_slot_ms,
+                         "cuda_core_slot_kernel_frac": k1_bytes / (k1_slot_ms * 1e-3) / 1e9 / peak},
             "pipeline": {"algorithmic_bytes_per_step": k1_bytes + k3_bytes, "achieved_gbs": (k1_bytes + k3_bytes) / (total_ms / K * 1e-3) / 1e9,
                          "frac_of_hbm_peak": (k1_bytes + k3_bytes) / (total_ms / K * 1e-3) / 1e9 / peak,
                          "k1_ms": k1_ms, "k3_ms": k3_ms,
