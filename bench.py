@@ -295,6 +295,114 @@ def c2_line(dev, peak):
             "refine_detections_1000x25_ms": timed(lambda: m.refine_detections_graph(det[0], det[1], det[2], window, cfg))}
 
 
+def cooperative_lines(dev, world, rank):
+    """The cooperative (strong-scaling) splits BASELINE.json names, measured at EVERY --gpus N so that the driver's SCALE record
+    carries them: all ranks work on the SAME scenes and the timed step includes the NCCL exchange.
+      c3_lstm_slab            config c3: one 8-view 64^3 scene, recurrent fusion C = F = 256, x-slabs + 1-voxel halo of h per step
+      c5_slab_owner           config c5: 32 scenes x 8 views, 96^3: every rank fuses all views for its x-slab, collapses the depth
+                              axis of its own ray samples linearly, all-reduce of PG [B,P,P,C], bias/BN/ReLU after the sum
+      c5_view_reduce_scatter  config c5 as BASELINE.json words it: views sharded, per-scene reduce-scatter of the partial grids by
+                              x-slab (pipelined against the next scene's unprojection), slab-local projection, all-reduce of rays
+    Each entry: ms_per_step (CUDA events, max over ranks), checksum, and the max error of scene 0 against the plain single-GPU
+    path computed in the same run by rank 0."""
+    import torch
+    import torch.distributed as dist
+    import mulit_view_object_detection_b200 as m
+    from mulit_view_object_detection_b200 import synthetic as syn, dist as mvd
+    out = {}
+    solo = None
+    if world > 1:
+        groups = [dist.new_group(ranks=[r]) for r in range(world)]        # collective: every rank creates every group
+        solo = groups[rank]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            r = fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), r
+
+    def rel_err(a, b):
+        return float(((a - b).abs() / (1e-5 * b.abs() + 1e-6)).max().item())
+
+    # ---- c3: recurrent fusion of one scene
+    V, C, X = 8, 256, 64
+    cfg = make_config(1)
+    feats, Rcam, Kmat = syn.make_scene(cfg, 1, V, T["fh"], T["fw"], C, seed=3000)
+    d = [torch.from_numpy(a).to(dev) for a in (feats, Rcam, Kmat)]
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    params = {"W": torch.randn((3, 3, 3, 2 * C, 4 * C), device=dev, generator=g) * (2.0 / (27 * 2 * C + 4 * C)) ** 0.5,
+              "b": torch.randn(4 * C, device=dev, generator=g) * 0.1}
+    ms, (rays, _) = timed(lambda: mvd.lstm_slab(*d, cfg, params, proj_size=T["P"]), steps=3, warmup=2)
+    err = None
+    if rank == 0 and world > 1:
+        ref, _ = mvd.lstm_slab(*d, cfg, params, proj_size=T["P"], group=solo)
+        err = float((rays - ref).abs().max().item())                       # the sharded recurrence is bit-identical by design
+    barrier()
+    flop = 2.0 * X ** 3 * 27 * 2 * C * 4 * C * V
+    out["c3_lstm_slab"] = {"workload": "c3: one 8-view 64^3 scene, ConvLSTM 3x3x3 C=F=256 (3xFP16 split on tcgen05), x-slabs + halo of h per step, proj_grid",
+                           "ms_per_step": ms, "useful_tflops": flop / ms / 1e9, "checksum": float(rays.double().sum()),
+                           "max_abs_err_vs_single_gpu": err, "exchange": "2 planes of h (4 MB each) per neighbour per view step (isend/irecv) + 4-byte all-reduce of the operand scale + all-reduce of the ray slices (32.8 MB)"}
+    del rays, params
+    torch.cuda.empty_cache()
+
+    # ---- c5: 32 scenes x 8 views, 96^3
+    Bc, Xc = 32, 96
+    from mulit_view_object_detection_b200.config import FusionConfig
+    cfg5 = FusionConfig(nvox=Xc, nvox_z=Xc, samples=T["S"], NUM_VIEWS=V, GRID_REAS="add", IMAGES_PER_GPU=Bc,
+                        IMAGE_SHAPE=np.array([T["image"], T["image"], 3]), TOP_DOWN_PYRAMID_SIZE=C)
+    feats, Rcam, Kmat = syn.make_scene(cfg5, Bc, V, T["fh"], T["fw"], C, seed=5000)
+    d = [torch.from_numpy(a).to(dev) for a in (feats, Rcam, Kmat)]
+    depth = {"weight": torch.full((T["S"],), 1.0 / T["S"], device=dev), "bias": 0.01, "bn": (1.1, 0.02, -0.01, 0.9)}
+    ms, (pg, _) = timed(lambda: mvd.slab_owner(*d, cfg5, T["P"], mode="sum", depth=depth), steps=3, warmup=2)
+    err = None
+    if rank == 0:
+        one = [t[:1].contiguous() for t in d]
+        fused = m.unproject_fuse(*one, cfg5, mode="sum")
+        ref = m.proj_grid_depth_sampling([fused, one[1], one[2]], cfg5, T["P"], "depth", params=depth)
+        err = rel_err(pg[:1], ref)
+        del fused, ref
+    barrier()
+    out["c5_slab_owner"] = {"workload": "c5: 32 scenes x 8 views, 96^3, slab owner + linear depth collapse per slab, PG [B,P,P,C] out",
+                            "ms_per_step": ms, "voxel_samples_per_s": Bc * V * Xc ** 3 / ms * 1e3, "checksum": float(pg.double().sum()),
+                            "max_err_vs_single_gpu_in_tolerance_units": err,
+                            "exchange": "one all-reduce of PG: %d scenes x 1.6 MB = %.0f MB" % (Bc, Bc * T["P"] * T["P"] * C * 4 / 1e6)}
+    del pg
+    torch.cuda.empty_cache()
+    if world <= V and Xc % world == 0:
+        ms, (rays, _) = timed(lambda: mvd.view_shard_reduce_scatter(*d, cfg5, T["P"], mode="sum"), steps=2, warmup=1)
+        err = None
+        if rank == 0:
+            one = [t[:1].contiguous() for t in d]
+            ref, _ = m.unproject_fuse_project(*one, cfg5, T["P"], mode="sum")
+            err = rel_err(rays[:1], ref)
+            del ref
+        barrier()
+        out["c5_view_reduce_scatter"] = {"workload": "c5: 32 scenes x 8 views, 96^3, views sharded, per-scene reduce-scatter of the partial grids "
+                                                     "by x-slab (pipelined), slab-local projection, all-reduce of ray slices",
+                                         "ms_per_step": ms, "voxel_samples_per_s": Bc * V * Xc ** 3 / ms * 1e3, "checksum": float(rays.double().sum()),
+                                         "max_err_vs_single_gpu_in_tolerance_units": err,
+                                         "exchange": "reduce-scatter of %.1f GB of partial grids per rank + all-reduce of %.2f GB of ray slices"
+                                                     % (Bc * Xc ** 3 * C * 4 / 1e9, Bc * T["S"] * T["P"] * T["P"] * C * 4 / 1e9)}
+        del rays
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -412,6 +520,12 @@ def run_b200(args):
     neck_value = voxel_samples_step * Ke / (float(tn.item()) * 1e-3)
     neck_checksum = float(n_out.double().sum())
 
+    coop = None
+    pipe_bytes, neck_bytes = (pipe.h2d_bytes, pipe.d2h_bytes), (neck.h2d_bytes, neck.d2h_bytes)
+    if not args.no_cooperative:
+        del grid, rays, pipe, neck, h_out, n_out
+        torch.cuda.empty_cache()
+        coop = cooperative_lines(dev, world, rank)
     if rank == 0:
         peak, peak_src = measured_peak()
         k1_bytes, k3_bytes = algorithmic_bytes(B)
@@ -422,10 +536,10 @@ def run_b200(args):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe_bytes[0], "d2h_bytes_per_step": pipe_bytes[1],
                     "steps": Ke, "api": "mvf_unproject_fuse_project_host (pinned host buffers, H2D + K1 + K3 + D2H + sync)",
                     "checksum": checksum},
-            "e2e_neck": {"value": neck_value, "unit": UNIT, "h2d_bytes_per_step": neck.h2d_bytes, "d2h_bytes_per_step": neck.d2h_bytes,
+            "e2e_neck": {"value": neck_value, "unit": UNIT, "h2d_bytes_per_step": neck_bytes[0], "d2h_bytes_per_step": neck_bytes[1],
                          "steps": Ke, "api": "mvf_fusion_neck_level_host (features in, depth-sampled PG [B,P,P,C] out: H2D + K1(+BN+ReLU) "
                                              "+ K3b + D2H + sync) -- the host/device boundary of the reference model; extra to `e2e`",
                          "checksum": neck_checksum},
@@ -443,6 +557,8 @@ def run_b200(args):
                          "k1_ms": k1_ms, "k3_ms": k3_ms,
                          "k3_achieved_gbs": k3_bytes / (k3_ms * 1e-3) / 1e9},
         }
+        if coop is not None:
+            line["cooperative"] = coop
         if world == 1 and not args.no_convlstm:
             line["k2_convlstm"] = convlstm_line(dev, local)
             line["c2_heads"] = c2_line(dev, peak)
@@ -542,6 +658,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-convlstm", action="store_true", help="skip the extra K2 (ConvLSTM on tensor cores) measurement")
+    ap.add_argument("--no-cooperative", action="store_true", help="skip the cooperative multi-GPU splits (c3 / c5 strong scaling)")
     ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner", "slab_owner_scatter", "lstm_slab"],
                     help="multi-GPU sharding: scene (default, weak scaling, no collective) or one of the cooperative "
                          "strategies of dist.py on a FIXED batch of --scenes scenes (strong scaling)")

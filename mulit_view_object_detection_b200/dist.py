@@ -30,13 +30,26 @@ import torch.distributed as dist
 class CudaOps:
     """The product path: kernels of libmvfusion.so on torch CUDA tensors."""
 
-    def unproject_fuse(self, feats, Rcam, Kmat, config, mode, Rmain=None, x_slab=None):
+    def unproject_fuse(self, feats, Rcam, Kmat, config, mode, Rmain=None, x_slab=None, tensor_cores=None):
         from . import layers
-        return layers.unproject_fuse(feats, Rcam, Kmat, config, mode=mode, Rmain=Rmain, x_slab=x_slab)
+        return layers.unproject_fuse(feats, Rcam, Kmat, config, mode=mode, Rmain=Rmain, x_slab=x_slab, tensor_cores=tensor_cores)
 
     def proj_grid(self, grid, Rcam, Kmat, config, proj_size, x_slab=None):
         from . import layers
         return layers.proj_grid([grid, Rcam, Kmat], config, proj_size, x_slab=x_slab)
+
+    def proj_collapse_linear(self, grid, Rcam, Kmat, config, proj_size, weight, x_slab=None):
+        """The LINEAR part of proj_grid + depth_sampling for one grid slab: sum_s w_s * sample_s, [B,P,P,C] (K3b without bias /
+        BatchNorm / ReLU).  Slabs add up exactly: a ray sample lies in exactly one slab, the others contribute 0."""
+        from . import layers
+        params = {"weight": weight, "bias": 0.0, "bn": None}
+        return layers.proj_grid_depth_sampling([grid, Rcam, Kmat], config, proj_size, "depth", params=params, x_slab=x_slab,
+                                               linear=True)
+
+    def depth_affine_relu(self, x, depth):
+        """ReLU(BN_scalar(x + bias)) of depth_sampling (model_multi.py:483-487), applied AFTER the cross-rank sum."""
+        from . import layers
+        return layers.depth_affine_relu(x, depth)
 
     def scale(self, grid, factor):
         """grid * factor through the view-reduce kernel (V=1, per-channel scale)."""
@@ -116,25 +129,56 @@ def _reduce_scatter_x(partial, op, group):
     return out
 
 
+def _pipelined(B, ws, compute, exchange, finish):
+    """Software pipeline over scenes: the collective of scene b runs (async, on the backend's own stream) while scene b+1 is
+    being unprojected on the compute stream.  ``compute(b)`` -> tensor, ``exchange(t)`` -> (tensor, work | None),
+    ``finish(b, t)`` consumes the exchanged tensor."""
+    pending = None
+    for b in range(B):
+        t = compute(b)
+        if pending is not None:
+            pb, pt, pw = pending
+            if pw is not None:
+                pw.wait()
+            finish(pb, pt)
+        if ws > 1:
+            t, w = exchange(t)
+        else:
+            w = None
+        pending = (b, t, w)
+    pb, pt, pw = pending
+    if pw is not None:
+        pw.wait()
+    finish(pb, pt)
+
+
 def view_shard_allreduce(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None):
     """``feats`` / ``Rcam`` hold ALL views on every rank (or at least this rank's slice is valid);
-    each rank unprojects views ``view_slice(V, rank, world)`` only.  Returns (rays, fused grid)."""
+    each rank unprojects views ``view_slice(V, rank, world)`` only, scene by scene, and the all-reduce of scene b overlaps the
+    unprojection of scene b+1.  Returns (rays, fused grid)."""
     ops = ops or CudaOps()
     rank, ws = world(group)
-    V = feats.shape[1]
+    B, V = feats.shape[0], feats.shape[1]
     lo, hi = view_slice(V, rank, ws)
     Rmain = Rcam[:, 0].contiguous()
     local_mode = "max" if mode == "max" else "sum"
-    if hi > lo:
-        partial = ops.unproject_fuse(feats[:, lo:hi].contiguous(), Rcam[:, lo:hi].contiguous(), Kmat, config,
-                                     local_mode, Rmain=Rmain)
-    else:                                                # more ranks than views: identity element
-        g = config
-        shape = (feats.shape[0], g.nvox, g.nvox, g.nvox_z, feats.shape[-1])
-        partial = torch.full(shape, float("-inf") if mode == "max" else 0.0, dtype=feats.dtype, device=feats.device)
-    fused = _all_reduce(partial, _reduce_op(mode), group)
-    if mode == "mean":
-        fused = ops.scale(fused, 1.0 / V)
+    g = config
+    fused = torch.empty((B, g.nvox, g.nvox, g.nvox_z, feats.shape[-1]), dtype=feats.dtype, device=feats.device)
+
+    def compute(b):
+        if hi > lo:
+            return ops.unproject_fuse(feats[b:b + 1, lo:hi].contiguous(), Rcam[b:b + 1, lo:hi].contiguous(), Kmat[b:b + 1], config,
+                                      local_mode, Rmain=Rmain[b:b + 1])
+        # more ranks than views: identity element
+        return torch.full((1,) + tuple(fused.shape[1:]), float("-inf") if mode == "max" else 0.0, dtype=feats.dtype, device=feats.device)
+
+    def exchange(t):
+        return t, dist.all_reduce(t, op=_reduce_op(mode), group=group, async_op=True)
+
+    def finish(b, t):
+        fused[b:b + 1].copy_(ops.scale(t, 1.0 / V) if mode == "mean" else t)
+
+    _pipelined(B, ws, compute, exchange, finish)
     rays = ops.proj_grid(fused, Rcam, Kmat, config, proj_size)
     return rays, fused
 
@@ -144,17 +188,33 @@ def view_shard_reduce_scatter(feats, Rcam, Kmat, config, proj_size, mode="sum", 
     all-reduce(sum) of the ray slices.  Returns (rays, this rank's grid slab)."""
     ops = ops or CudaOps()
     rank, ws = world(group)
-    V = feats.shape[1]
+    B, V = feats.shape[0], feats.shape[1]
     lo, hi = view_slice(V, rank, ws)
     if hi <= lo:
         raise ValueError("view sharding needs at least one view per rank (V=%d, world=%d)" % (V, ws))
+    if config.nvox % ws:
+        raise ValueError("reduce-scatter by slab needs nvox (%d) divisible by the world size (%d)" % (config.nvox, ws))
     Rmain = Rcam[:, 0].contiguous()
-    partial = ops.unproject_fuse(feats[:, lo:hi].contiguous(), Rcam[:, lo:hi].contiguous(), Kmat, config,
-                                 "max" if mode == "max" else "sum", Rmain=Rmain)
-    slab = _reduce_scatter_x(partial, _reduce_op(mode), group)
-    if mode == "mean":
-        slab = ops.scale(slab, 1.0 / V)
     xb, xc = slab_bounds(config.nvox, rank, ws)
+    g = config
+    slab = torch.empty((B, xc, g.nvox, g.nvox_z, feats.shape[-1]), dtype=feats.dtype, device=feats.device)
+    gloo = ws > 1 and dist.get_backend(group) == "gloo"                    # gloo has no reduce_scatter: reduce, then slice
+
+    def compute(b):
+        return ops.unproject_fuse(feats[b:b + 1, lo:hi].contiguous(), Rcam[b:b + 1, lo:hi].contiguous(), Kmat[b:b + 1], config,
+                                  "max" if mode == "max" else "sum", Rmain=Rmain[b:b + 1])
+
+    def exchange(t):                                                        # per scene the x-slabs are contiguous chunks
+        if gloo:
+            return t, dist.all_reduce(t, op=_reduce_op(mode), group=group, async_op=True)
+        out = torch.empty((1, xc) + tuple(t.shape[2:]), dtype=t.dtype, device=t.device)
+        return out, dist.reduce_scatter_tensor(out[0], t[0], op=_reduce_op(mode), group=group, async_op=True)
+
+    def finish(b, t):
+        part = t[:, xb:xb + xc] if (gloo or ws == 1) else t
+        slab[b:b + 1].copy_(ops.scale(part.contiguous(), 1.0 / V) if mode == "mean" else part)
+
+    _pipelined(B, ws, compute, exchange, finish)
     rays = ops.proj_grid(slab, Rcam, Kmat, config, proj_size, x_slab=(xb, xc))
     rays = _all_reduce(rays, dist.ReduceOp.SUM, group)
     return rays, slab
@@ -177,15 +237,25 @@ def _reduce_scatter_scenes(rays, group):
     return out
 
 
-def slab_owner(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None, scatter_scenes=False):
+def slab_owner(feats, Rcam, Kmat, config, proj_size, mode="sum", group=None, ops=None, scatter_scenes=False, depth=None):
     """Owner-computes: every rank holds all views and fuses ALL of them for its own x-slab;
     the only exchange is the all-reduce(sum) of the ray slices -- or, with ``scatter_scenes``, a reduce-scatter that
     leaves rank r with the ray slices of scenes [r*B/W, (r+1)*B/W) only (the downstream heads are data parallel over
-    scenes).  Returns (rays, grid slab)."""
+    scenes).  Returns (rays, grid slab).
+
+    ``depth`` = the depth_sampling learnables ({'weight' [S], 'bias', 'bn'}, model_multi.py:481-487): the neck's real boundary.
+    The depth collapse is linear up to its bias, so each rank collapses its own slab's samples (K3b, no bias / BN / ReLU),
+    the all-reduce moves [B,P,P,C] (1.6 MB per T-scene instead of 32.8 MB of mostly-zero ray slices), and bias + BatchNorm +
+    ReLU are applied after the sum.  Returns (PG [B,P,P,C], grid slab).  A rank whose slab is empty (more ranks than x-planes)
+    contributes zeros."""
     ops = ops or CudaOps()
     rank, ws = world(group)
     xb, xc = slab_bounds(config.nvox, rank, ws)
     slab = ops.unproject_fuse(feats, Rcam, Kmat, config, mode, x_slab=(xb, xc))
+    if depth is not None:
+        pg = ops.proj_collapse_linear(slab, Rcam, Kmat, config, proj_size, depth["weight"], x_slab=(xb, xc))
+        pg = _reduce_scatter_scenes(pg, group) if scatter_scenes else _all_reduce(pg, dist.ReduceOp.SUM, group)
+        return ops.depth_affine_relu(pg, depth), slab
     rays = ops.proj_grid(slab, Rcam, Kmat, config, proj_size, x_slab=(xb, xc))
     rays = _reduce_scatter_scenes(rays, group) if scatter_scenes else _all_reduce(rays, dist.ReduceOp.SUM, group)
     return rays, slab
@@ -262,8 +332,10 @@ def lstm_slab(feats, Rcam, Kmat, config, params, proj_size=None, group=None, ops
     h = c = None
     for t in range(V):
         # view t unprojected for the slab and its halo planes; a 1-view 'sum' is the per-view grid itself
+        # (slot kernel: its per-voxel arithmetic does not depend on the slab, which keeps the sharded recurrence bit-identical
+        # to the unsharded one at every world size)
         x_t = ops.unproject_fuse(feats[:, t:t + 1].contiguous(), Rcam[:, t:t + 1].contiguous(), Kmat, config, "sum",
-                                 Rmain=Rmain, x_slab=(xb - lo, xc + lo + hi))
+                                 Rmain=Rmain, x_slab=(xb - lo, xc + lo + hi), tensor_cores=False)
         # the fp16 operand split scales by a power of two taken from max|operand|: agree on it across the slabs
         # (4-byte all-reduce) so that the sharded recurrence is bit-identical to the unsharded one
         amax = x_t.amax().clamp_min(0).reshape(1)

@@ -654,7 +654,7 @@ def _depth_params(name, params, S, device):
     if w.numel() != S:
         raise ValueError("depth conv weight must have S=%d entries" % S)
     bias = float(p.get("bias", 0.0))
-    gamma, beta, mean, var = (float(np.asarray(a).reshape(-1)[0]) for a in p.get("bn", (1.0, 0.0, 0.0, 1.0)))
+    gamma, beta, mean, var = (float(np.asarray(a).reshape(-1)[0]) for a in (p.get("bn") or (1.0, 0.0, 0.0, 1.0)))
     inv = np.float32(np.float32(1.0) / np.sqrt(np.float32(var) + np.float32(BN_EPS))) * np.float32(gamma)
     shift = np.float32(beta) - np.float32(mean) * inv
     return w, bias, float(inv), float(shift)
@@ -677,16 +677,35 @@ def depth_sampling(x, config, name, params=None):
     return out
 
 
-def proj_grid_depth_sampling(inputs, config, proj_size, name, params=None, view=0, x_slab=None):
-    """Fused ``depth_sampling(proj_grid(...))``: the ray slices [B,S,P,P,C] are never written."""
+def depth_affine_relu(x, depth):
+    """ReLU(BN_scalar(x + bias)): the non-linear tail of depth_sampling (model_multi.py:483-487) on an already collapsed
+    [B,P,P,C] tensor (mvf_depth_collapse with S = 1, weight 1)."""
+    x = _cuda(x, "x")
+    B, P1, P2, Cc = x.shape
+    one = torch.ones(1, dtype=torch.float32, device=x.device)
+    p = dict(depth)
+    p["weight"] = one
+    w, bias, inv, shift = _depth_params("depth", p, 1, x.device)
+    out = torch.empty_like(x)
+    rc = lib.mvf_depth_collapse(_ptr(x), B, 1, P1 * P2, Cc, _ptr(w), bias, inv, shift, _lib.FLAG_RELU_OUT, _ptr(out), _stream())
+    check(rc, "mvf_depth_collapse")
+    return out
+
+
+def proj_grid_depth_sampling(inputs, config, proj_size, name, params=None, view=0, x_slab=None, linear=False):
+    """Fused ``depth_sampling(proj_grid(...))``: the ray slices [B,S,P,P,C] are never written.
+    ``linear``: only the linear part ``sum_s w_s * sample_s`` (no bias, BatchNorm or ReLU) -- what one grid slab contributes;
+    slabs add up and ``depth_affine_relu`` finishes the layer after the cross-rank sum (dist.slab_owner)."""
     grid, Rcam, Kmat = inputs
     grid, Rview, Rmain, Kmat, gp, g, B, Cc, ph, pw, flags, gd, xb, xc = _proj_common(
         grid, Rcam, Kmat, config, proj_size, view, x_slab, None)
     S = int(config.samples)
     w, bias, inv, shift = _depth_params(name, params, S, grid.device)
+    if linear:
+        bias, inv, shift = 0.0, 1.0, 0.0
     out = torch.empty((B, ph, pw, Cc), dtype=torch.float32, device=grid.device)
     rc = lib.mvf_project_depth_collapse(_ptr(grid), _ptr(Rview), _ptr(Rmain), _ptr(Kmat), None, C.byref(g), B, Cc,
-                                        _image_hw(config)[0], ph, pw, S, flags | _lib.FLAG_RELU_OUT, gd, xb, xc,
+                                        _image_hw(config)[0], ph, pw, S, flags | (0 if linear else _lib.FLAG_RELU_OUT), gd, xb, xc,
                                         _ptr(w), bias, inv, shift, _ptr(out), _stream())
     check(rc, "mvf_project_depth_collapse")
     return out

@@ -17,7 +17,7 @@ from helpers import small_cfg, scene
 class OracleOps:
     """dist.py's ``ops`` interface on torch CPU tensors, backed by the NumPy oracle."""
 
-    def unproject_fuse(self, feats, Rcam, Kmat, config, mode, Rmain=None, x_slab=None):
+    def unproject_fuse(self, feats, Rcam, Kmat, config, mode, Rmain=None, x_slab=None, tensor_cores=None):
         f, R, K = feats.numpy(), Rcam.numpy(), Kmat.numpy()
         if Rmain is not None:                       # oracle takes the main pose as view 0: prepend it with zero features
             R = np.concatenate([Rmain.numpy()[:, None], R], axis=1)
@@ -37,6 +37,17 @@ class OracleOps:
             full[:, x_slab[0]:x_slab[0] + x_slab[1]] = g
             g = full
         return torch.from_numpy(oracle.proj_grid(g, Rcam.numpy(), Kmat.numpy(), config, proj_size))
+
+    def proj_collapse_linear(self, grid, Rcam, Kmat, config, proj_size, weight, x_slab=None):
+        rays = self.proj_grid(grid, Rcam, Kmat, config, proj_size, x_slab=x_slab).numpy()          # [B,S,P,P,C]
+        w = np.asarray(weight, np.float32).reshape(1, -1, 1, 1, 1)
+        return torch.from_numpy((rays * w).sum(axis=1, dtype=np.float32))
+
+    def depth_affine_relu(self, x, depth):
+        gamma, beta, mean, var = (np.float32(np.asarray(a).reshape(-1)[0]) for a in depth["bn"])
+        inv = np.float32(1.0) / np.sqrt(var + np.float32(1e-3)) * gamma
+        y = (x.numpy() + np.float32(depth["bias"])) * inv + (beta - mean * inv)
+        return torch.from_numpy(np.maximum(y, 0).astype(np.float32))
 
     def scale(self, grid, factor):
         return grid * np.float32(factor)
@@ -72,6 +83,9 @@ class OracleCell:
         return torch.from_numpy(h_out), torch.from_numpy(np.ascontiguousarray(c[:, lo:Xin - hi]))
 
 
+DEPTH = {"weight": np.array([0.4, 0.3, 0.2, 0.1], np.float32), "bias": 0.05, "bn": (1.2, 0.1, -0.05, 0.8)}
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -95,6 +109,12 @@ def _worker(rank, world_size, port, strategy, mode, out_dir):
             rays = mvd.fuse_project_auto(*t, cfg, 10, mode=mode, ops=ops)                       # 2 scenes, 2 ranks: scene sharding
             one = mvd.fuse_project_auto(*[x[:1] for x in t], cfg, 10, mode=mode, ops=ops)         # 1 scene, 2 ranks: slab owner
             assert torch.allclose(one, rays[:1], rtol=1e-5, atol=1e-6)
+        elif strategy == "slab_owner_depth":
+            rays, _ = mvd.slab_owner(*t, cfg, 10, mode=mode, ops=ops, depth=DEPTH)
+        elif strategy == "slab_owner_depth_empty":                       # more ranks than x-planes: rank 2 owns an empty slab
+            cfg = small_cfg(nvox=2, nvox_z=6, samples=4, NUM_VIEWS=3)
+            rays, slab = mvd.slab_owner(*t, cfg, 10, mode=mode, ops=ops, depth=DEPTH)
+            assert slab.shape[1] == (1 if rank < 2 else 0)
         elif strategy == "slab_owner_scatter":
             part, _ = mvd.slab_owner(*t, cfg, 10, mode=mode, ops=ops, scatter_scenes=True)   # rank r keeps scene r
             parts = [torch.empty_like(part) for _ in range(world_size)]
@@ -178,3 +198,19 @@ def test_partition_helpers():
         assert spans[0][0] == 0 and sum(c for _, c in spans) == X
         assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(W - 1))
     assert mvd.scene_indices(7, 1, 3) == [1, 4]
+
+
+@pytest.mark.parametrize("strategy,world_size,nvox", [("slab_owner_depth", 2, 8), ("slab_owner_depth", 3, 8), ("slab_owner_depth_empty", 3, 2)])
+def test_slab_owner_with_depth_collapse(strategy, world_size, nvox, tmp_path):
+    """dist.slab_owner(depth=...): each rank collapses its own slab's ray samples linearly, the all-reduce moves [B,P,P,C], bias +
+    BatchNorm + ReLU follow the sum -- equal to depth_sampling(proj_grid(full grid)) (model_multi.py:481-487); also with an EMPTY
+    slab (more ranks than x-planes)."""
+    mp.spawn(_worker, args=(world_size, _free_port(), strategy, "sum", str(tmp_path)), nprocs=world_size, join=True)
+    cfg = small_cfg(nvox=nvox, nvox_z=6, samples=4, NUM_VIEWS=3)
+    feats, Rcam, Kmat = scene(small_cfg(nvox=8, nvox_z=6, samples=4, NUM_VIEWS=3), 2, 3, 12, 12, 8, seed=5)
+    fused = oracle.fuse_views(oracle.unproj_feat(feats, Rcam, Kmat, cfg), "sum")
+    ref = oracle.depth_sampling(oracle.proj_grid(fused, Rcam, Kmat, cfg, 10), DEPTH["weight"], DEPTH["bias"], DEPTH["bn"])
+    for r in range(world_size):
+        got = np.load(os.path.join(str(tmp_path), "rays_%d.npy" % r))
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6)
+    assert (ref > 0).any()

@@ -36,6 +36,12 @@ def _worker(rank, world_size, port, out_dir):
                          ("slab_owner", mvd.slab_owner)):
             rays, _ = fn(*d, cfg, 24, mode="sum")
             res[name] = float((rays - ref).abs().max() / ref.abs().max())
+        # slab owner with the depth collapse: linear collapse per slab, all-reduce of PG, bias / BN / ReLU after the sum
+        depth = {"weight": torch.linspace(0.3, 0.05, 6).cuda(), "bias": 0.02, "bn": (1.1, 0.05, -0.02, 0.9)}
+        fused_ref = m.unproject_fuse(*d, cfg, mode="sum")
+        pg_ref = m.proj_grid_depth_sampling([fused_ref, d[1], d[2]], cfg, 24, "depth", params=depth)
+        pg, _ = mvd.slab_owner(*d, cfg, 24, mode="sum", depth=depth)
+        res["slab_owner_depth"] = float((pg - pg_ref).abs().max() / pg_ref.abs().max())
         rays, _ = mvd.scene_shard(*d, cfg, 24, mode="sum", gather=True)
         res["scene"] = float((rays - ref).abs().max())
         refm, _ = m.unproject_fuse_project(*d, cfg, 24, mode="max")
@@ -67,8 +73,9 @@ def test_nccl_strategies_match_single_gpu(tmp_path):
         pytest.skip("needs 2 GPUs")
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
-        allreduce, lstm_rays, lstm_slab, max_exact, reduce_scatter, scene_err, slab_owner = \
+        allreduce, lstm_rays, lstm_slab, max_exact, reduce_scatter, scene_err, slab_owner, slab_owner_depth = \
             np.load(os.path.join(str(tmp_path), "res_%d.npy" % r))
+        assert slab_owner_depth < 1e-5
         assert lstm_slab == 0.0 and lstm_rays == 0.0        # same tiles, same K order: bit-identical to the unsharded run
         assert allreduce < 1e-5 and reduce_scatter < 1e-5 and slab_owner < 1e-5      # partial-sum order differs
         assert scene_err == 0.0 and max_exact == 0.0
