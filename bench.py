@@ -415,6 +415,15 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    # bind the rank to the CPUs (hence, by first touch, the pinned pages) of its GPU's NUMA node before anything is allocated
+    numa_node = None
+    if not args.no_numa_bind:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        try:
+            from pcie_probe import bind_to_gpu_numa
+            numa_node = bind_to_gpu_numa(local)
+        except Exception:
+            numa_node = None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -538,7 +547,12 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe_bytes[0], "d2h_bytes_per_step": pipe_bytes[1],
                     "steps": Ke, "api": "mvf_unproject_fuse_project_host (pinned host buffers, H2D + K1 + K3 + D2H + sync)",
-                    "checksum": checksum},
+                    "checksum": checksum,
+                    "bound": "host link: %.0f MB cross PCIe per rank per step (%.1f GB/s per rank achieved here, both directions "
+                             "together); see profiles/r2_pcie_probe.json for the measured copy ceiling at 1/2/4/8 ranks"
+                             % ((pipe_bytes[0] + pipe_bytes[1]) / 1e6,
+                                (pipe_bytes[0] + pipe_bytes[1]) * world / 1e9 / (voxel_samples_step / e2e_value) / world),
+                    "numa_node": numa_node},
             "e2e_neck": {"value": neck_value, "unit": UNIT, "h2d_bytes_per_step": neck_bytes[0], "d2h_bytes_per_step": neck_bytes[1],
                          "steps": Ke, "api": "mvf_fusion_neck_level_host (features in, depth-sampled PG [B,P,P,C] out: H2D + K1(+BN+ReLU) "
                                              "+ K3b + D2H + sync) -- the host/device boundary of the reference model; extra to `e2e`",
@@ -658,6 +672,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-convlstm", action="store_true", help="skip the extra K2 (ConvLSTM on tensor cores) measurement")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-cooperative", action="store_true", help="skip the cooperative multi-GPU splits (c3 / c5 strong scaling)")
     ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner", "slab_owner_scatter", "lstm_slab"],
                     help="multi-GPU sharding: scene (default, weak scaling, no collective) or one of the cooperative "

@@ -1,16 +1,16 @@
 #!/bin/bash
-# usage: tools/run_scaling.sh N OUTDIR  -- runs, on N GPUs of one box: the headline bench (scene sharding, weak scaling),
-# config c3 (recurrent fusion over x-slabs) and config c5 (32 scenes, 96^3, reduce-scatter by slab / slab owner; strong scaling)
-N=$1; OUT=$2; mkdir -p $OUT
-if [ "$N" = "1" ]; then L="python"; else L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"; fi
-$L bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline --no-convlstm > $OUT/scene_$N.json 2> $OUT/scene_$N.err
-$L bench.py --gpus $N --strategy lstm_slab --scenes 1 --steps 2 --warmup 1 > $OUT/c3_lstm_slab_$N.json 2> $OUT/c3_lstm_slab_$N.err
-for st in view_reduce_scatter slab_owner view_allreduce; do
-  $L bench.py --gpus $N --strategy $st --scenes 32 --nvox 96 --steps 3 --warmup 3 > $OUT/c5_${st}_$N.json 2> $OUT/c5_${st}_$N.err
+# One 8-GPU box: host-link probe at 2/4/8 ranks (with and without NUMA binding) and bench.py at 4 and 8 ranks.
+# usage (GPU box): bash tools/run_scaling.sh <outdir>
+OUT=${1:-gpurun_out/r2d}; mkdir -p $OUT
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+nvidia-smi topo -m > $OUT/topo.txt 2>&1; lscpu | grep -i "numa\|socket\|^CPU(s)" >> $OUT/topo.txt
+python tools/pcie_probe.py > $OUT/probe_n1.json 2>/dev/null
+for N in 2 4 8; do
+  $TR --nproc-per-node $N --master-port 2951$N tools/pcie_probe.py > $OUT/probe_n$N.json 2>/dev/null
+  $TR --nproc-per-node $N --master-port 2952$N tools/pcie_probe.py --numa > $OUT/probe_n${N}_numa.json 2>/dev/null
 done
-tail -c 300 $OUT/*_$N.err
-for f in $OUT/*_$N.json; do echo $f; python -c "
-import json,sys
-try:
-    d=json.loads(open('$f').read().strip().splitlines()[-1]); print({k:d.get(k) for k in ('value','n_gpus','ms_per_step','scaling','useful_tflops')})
-except Exception as e: print('ERR',e)"; done
+for N in 8 4; do
+  timeout 400 $TR --nproc-per-node $N --master-port 2953$N bench.py --gpus $N --steps 5 --warmup 3 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err
+done
+timeout 300 $TR --nproc-per-node 8 --master-port 29549 bench.py --gpus 8 --steps 5 --warmup 3 --no-numa-bind --no-cooperative > $OUT/bench_n8_nonuma.json 2> $OUT/bench_n8_nonuma.err
+cat $OUT/probe_n*.json
