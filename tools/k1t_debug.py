@@ -74,8 +74,8 @@ def prof():
     _lib.lib.mvf_debug_k1t_prof.restype = ctypes.c_int
     assert _lib.lib.mvf_debug_k1t_prof(buf) == 0
     v = list(buf)
-    names = {0: "compute half0 [total, phaseA+bbox, empty-wait, produce, header, ksteps, tma-issue, fence+arrive]", 8: "compute half1", 16: "MMA h0 [total, full-wait, acc_empty-wait, ksteps, header-wait]",
-             24: "epilogue g0 [total, acc_full-wait, staging-wait, work]"}
+    names = {0: "compute half0 [total, phaseA+bbox, empty-wait, produce, header, ksteps, tma-issue, fence+arrive]", 8: "compute half1", 16: "MMA h0 [total, full-wait, acc_empty-wait, ksteps, header-wait, fence+desc, 3 mma issue, commit]",
+             24: "epilogue w0 [total, acc_full-wait, -, work, wait_read, tmem wait::ld, scale+st.shared, fence+syncwarp+tma store]"}
     for base, nm in names.items():
         print("%-70s %s" % (nm, v[base:base + 8]))
 
