@@ -26,6 +26,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     } while (!done);
 }
+// Wait with the retry loop INSIDE the asm statement: no C++-level loop on an asm result, so a warp that executes it convergently stays
+// convergent in the compiler's eyes and warp-uniform values keep living in uniform registers (what tcgen05 / TMA instructions take).
+__device__ __forceinline__ void mbar_wait_conv(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
+                 :: "r"(bar), "r"(parity) : "memory");
+}
+// one lane of a convergent warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // non-blocking probe: issue it early and test the result late, so the shared-memory round trip overlaps other work
 __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t done;
