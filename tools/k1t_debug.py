@@ -46,14 +46,18 @@ def timing():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        n = 10
+        n = 30
         for _ in range(n):
             m.unproject_fuse(*d, cfg, mode="sum", out=grid, tensor_cores=tc)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        print("timing tensor_cores=%s: %.3f ms per %d scenes = %.1f us/scene -> %.3f of 6560 GB/s" %
-              (tc, ms, B, ms * 1e3 / B, (1024.0 * (12800 + 262144) * B / (ms * 1e-3) / 1e9) / 6560.0), flush=True)
+        try:
+            clk = torch.cuda.clock_rate()
+        except Exception:
+            clk = -1
+        print("timing tensor_cores=%s: %.3f ms per %d scenes = %.1f us/scene -> %.3f of 6560 GB/s  (SM clock after the loop %d MHz)" %
+              (tc, ms, B, ms * 1e3 / B, (1024.0 * (12800 + 262144) * B / (ms * 1e-3) / 1e9) / 6560.0, clk), flush=True)
 
 
 def prof():
@@ -74,8 +78,9 @@ def prof():
     _lib.lib.mvf_debug_k1t_prof.restype = ctypes.c_int
     assert _lib.lib.mvf_debug_k1t_prof(buf) == 0
     v = list(buf)
-    names = {0: "compute half0 [total, phaseA+bbox, empty-wait, produce, header, ksteps, tma-issue, fence+arrive]", 8: "compute half1", 16: "MMA h0 [total, full-wait, acc_empty-wait, ksteps, header-wait, fence+desc, 3 mma issue, commit]",
-             24: "epilogue w0 [total, acc_full-wait, -, work, wait_read, tmem wait::ld, scale+st.shared, fence+syncwarp+tma store]"}
+    names = {0: "producer g0 [total, record wait, ring-slot wait, produce, -, K-steps, -, fence+arrive]", 8: "producer g1",
+             16: "geometry [total, record-slot wait] / MMA warp [total, full wait, acc_empty wait, record wait]",
+             24: "epilogue w0 [total, acc_full wait, -, work, wait_read, tmem wait::ld, scale+st.shared, fence+syncwarp+tma store]"}
     for base, nm in names.items():
         print("%-70s %s" % (nm, v[base:base + 8]))
 
