@@ -19,18 +19,23 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+// MVF_MBAR_HINT (ns): suspend-time hint of try_wait -- the waiting warp sleeps in hardware until the phase completes instead of
+// re-polling the barrier through the shared-memory pipe (K1T: ~20 % of the LSU data pipe was spent on polls)
+#ifndef MVF_MBAR_HINT
+#define MVF_MBAR_HINT 1000000
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(MVF_MBAR_HINT) : "memory");
     } while (!done);
 }
 // Wait with the retry loop INSIDE the asm statement: no C++-level loop on an asm result, so a warp that executes it convergently stays
 // convergent in the compiler's eyes and warp-uniform values keep living in uniform registers (what tcgen05 / TMA instructions take).
 __device__ __forceinline__ void mbar_wait_conv(uint32_t bar, uint32_t parity) {
-    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
-                 :: "r"(bar), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
+                 :: "r"(bar), "r"(parity), "r"(MVF_MBAR_HINT) : "memory");
 }
 // one lane of a convergent warp
 __device__ __forceinline__ bool elect_one() {
