@@ -7,8 +7,8 @@
 // (ties -> lower index), IoU on min/max-normalised corners with individually rounded fp32
 // ops, area <= 0 -> IoU 0, suppress iff IoU > threshold.
 //
-// Pipeline per problem:  keys (score, index) -> bitonic sort (shared memory for <= 4096-key
-// chunks, global compare-exchange above) -> gather boxes into score order -> IoU bit matrix,
+// Pipeline per problem:  keys (score, index) -> counting sort (<= 8192 keys; the ProposalLayer's top-k over all anchors keeps the
+// bitonic network) -> boxes scattered into score order -> IoU bit matrix,
 // one __ballot_sync word per (row, 32 columns) -> one-CTA greedy scan over 32-row blocks.
 // The per-class NMS of the detection head is ONE pass: a bit is set only between boxes of
 // the same class and the scan keeps per-class counters (= map_fn over classes, :1166-1187).
@@ -27,6 +27,9 @@ __device__ __forceinline__ unsigned score_key_desc(float s) {
     return ~asc;                                                  // ascending key == descending score
 }
 __device__ __forceinline__ u64 make_key(float s, unsigned idx) { return ((u64)score_key_desc(s) << 32) | idx; }
+// excluded boxes sort behind every candidate; the index keeps the key unique (the counting sort below ranks by strict comparison)
+__device__ __forceinline__ u64 excluded_key(unsigned idx) { return (0xFFFFFFFFull << 32) | idx; }
+__device__ __forceinline__ bool is_excluded(u64 key) { return (key >> 32) == 0xFFFFFFFFull; }
 
 __device__ __forceinline__ void cmpx(u64& a, u64& b, bool asc) {
     if ((a > b) == asc) { const u64 t = a; a = b; b = t; }
@@ -110,167 +113,229 @@ __device__ __forceinline__ Box clip_box(Box b, float wy1, float wx1, float wy2, 
     r.y2 = fmaxf(fminf(b.y2, wy2), wy1); r.x2 = fmaxf(fminf(b.x2, wx2), wx1);
     return r;
 }
-__device__ __forceinline__ bool iou_above(const float4 a, const float4 b, float thr) {
-    const float ymin_i = fminf(a.x, a.z), ymax_i = fmaxf(a.x, a.z), xmin_i = fminf(a.y, a.w), xmax_i = fmaxf(a.y, a.w);
-    const float ymin_j = fminf(b.x, b.z), ymax_j = fmaxf(b.x, b.z), xmin_j = fminf(b.y, b.w), xmax_j = fmaxf(b.y, b.w);
-    const float area_i = mul_rn(sub_rn(ymax_i, ymin_i), sub_rn(xmax_i, xmin_i));
-    const float area_j = mul_rn(sub_rn(ymax_j, ymin_j), sub_rn(xmax_j, xmin_j));
-    if (area_i <= 0.f || area_j <= 0.f) return false;
-    const float iy0 = fmaxf(ymin_i, ymin_j), ix0 = fmaxf(xmin_i, xmin_j);
-    const float iy1 = fminf(ymax_i, ymax_j), ix1 = fminf(xmax_i, xmax_j);
-    const float inter = mul_rn(fmaxf(sub_rn(iy1, iy0), 0.f), fmaxf(sub_rn(ix1, ix0), 0.f));
-    const float iou = div_rn(inter, sub_rn(add_rn(area_i, area_j), inter));
-    return iou > thr;
-}
-
 // ---- NMS stages --------------------------------------------------------------------------------
 // A class id outside [0, MVF_MAX_CLASSES) would index the scan's shared per-class counters out of bounds: such a box gets the
 // EXCLUDED key here, so it sorts behind every candidate (never kept, suppresses nothing) -- the documented contract of mvf_nms.
-__global__ void nms_keys_kernel(const float* scores, const int32_t* class_ids, u64* keys, int n, int n_pad) {
+__global__ void nms_keys_kernel(const float* scores, const int32_t* class_ids, u64* keys, int32_t* rank, int n, int n_pad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int pb = blockIdx.y;
     if (i >= n_pad) return;
     bool ok = i < n;
     if (ok && class_ids) { const int c = class_ids[(size_t)pb * n + i]; ok = c >= 0 && c < MVF_MAX_CLASSES; }
-    keys[(size_t)pb * n_pad + i] = ok ? make_key(scores[(size_t)pb * n + i], (unsigned)i) : KEY_EXCLUDED;
+    keys[(size_t)pb * n_pad + i] = ok ? make_key(scores[(size_t)pb * n + i], (unsigned)i) : excluded_key((unsigned)i);
+    if (rank && i < n) rank[(size_t)pb * n + i] = 0;
 }
 
-// sorted position r -> (original index | -1, box, class)
-__global__ void nms_gather_kernel(const u64* keys, const float4* boxes, const int32_t* class_ids, int n, int n_pad,
-                                  int32_t* s_idx, float4* s_box, int32_t* s_cls) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int pb = blockIdx.y;
-    if (r >= n) return;
-    const u64 key = keys[(size_t)pb * n_pad + r];
-    const size_t o = (size_t)pb * n + r;
-    if (key == KEY_EXCLUDED) { s_idx[o] = -1; s_box[o] = make_float4(0.f, 0.f, 0.f, 0.f); s_cls[o] = -1; return; }
-    const unsigned idx = (unsigned)(key & 0xFFFFFFFFu);
-    s_idx[o] = (int)idx;
-    s_box[o] = boxes[(size_t)pb * n + idx];
-    s_cls[o] = class_ids ? class_ids[(size_t)pb * n + idx] : 0;
-}
-
-constexpr int MASK_ROWS = 64;    // rows per CTA (8 warps x 8 rows)
-
-// bit (r, c) = c > r  &&  same class  &&  IoU(r, c) > thr   -- one ballot word per (row, 32 columns)
+// ---- counting sort for <= 8192 keys: rank(i) = #{j : key_j < key_i} (keys are unique), computed as RANK_SPLIT partial counts per
+// element over slices of j and combined with atomicAdd; one pass over n^2 / 2^17 comparisons per SM instead of the bitonic network's
+// launches (6000 keys: ~5 us instead of 56 us).  The scatter kernel then writes the score-ordered arrays directly.
+constexpr int RANK_SPLIT = 8;
 __global__ void __launch_bounds__(256)
-nms_mask_kernel(const float4* s_box, const int32_t* s_cls, int n, int nwords, float thr, unsigned* mask) {
+nms_rank_kernel(const u64* keys, int n, int n_pad, int32_t* rank) {
+    __shared__ u64 tile[256];
+    const int pb = blockIdx.z;
+    const u64* kp = keys + (size_t)pb * n_pad;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const u64 mine = i < n ? kp[i] : 0ull;
+    const int per = (n + RANK_SPLIT - 1) / RANK_SPLIT;
+    const int j0 = blockIdx.y * per, j1 = min(n, j0 + per);
+    int cnt = 0;
+    for (int jb = j0; jb < j1; jb += 256) {
+        const int j = jb + threadIdx.x;
+        __syncthreads();
+        tile[threadIdx.x] = j < j1 ? kp[j] : ~0ull;              // pad: never smaller than a real key
+        __syncthreads();
+#pragma unroll 8
+        for (int t = 0; t < 256; ++t) cnt += tile[t] < mine;     // broadcast reads
+    }
+    if (i < n && cnt) atomicAdd(rank + (size_t)pb * n + i, cnt);
+}
+// element i -> sorted position rank(i): (original index | -1, box, class)
+__global__ void nms_scatter_kernel(const u64* keys, const int32_t* rank, const float4* boxes, const int32_t* class_ids, int n, int n_pad,
+                                   int32_t* s_idx, float4* s_box, int32_t* s_cls) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pb = blockIdx.y;
+    if (i >= n) return;
+    const u64 key = keys[(size_t)pb * n_pad + i];
+    const size_t o = (size_t)pb * n + rank[(size_t)pb * n + i];
+    if (is_excluded(key)) { s_idx[o] = -1; s_box[o] = make_float4(0.f, 0.f, 0.f, 0.f); s_cls[o] = -1; return; }
+    s_idx[o] = i;
+    s_box[o] = boxes[(size_t)pb * n + i];
+    s_cls[o] = class_ids ? class_ids[(size_t)pb * n + i] : 0;
+}
+static int rank_scatter(const u64* keys, int32_t* rank, const float4* boxes, const int32_t* class_ids, int nprob, int n, int n_pad,
+                        int32_t* s_idx, float4* s_box, int32_t* s_cls, cudaStream_t s) {
+    nms_rank_kernel<<<dim3((n + 255) / 256, RANK_SPLIT, nprob), 256, 0, s>>>(keys, n, n_pad, rank);
+    count_launch();
+    nms_scatter_kernel<<<dim3((n + 255) / 256, nprob), 256, 0, s>>>(keys, rank, boxes, class_ids, n, n_pad, s_idx, s_box, s_cls);
+    count_launch();
+    return check_launch();
+}
+
+constexpr int MASK_ROWS = 256;   // rows per CTA (8 warps x 32 rows), staged once in shared memory
+
+// min/max-normalised corners (tf.image.non_max_suppression accepts either corner order) and the area, as iou_above computes them
+struct NBox { float ymin, xmin, ymax, xmax, area; int cls; };
+__device__ __forceinline__ NBox norm_box(const float4 a, int cls) {
+    NBox b;
+    b.ymin = fminf(a.x, a.z); b.ymax = fmaxf(a.x, a.z); b.xmin = fminf(a.y, a.w); b.xmax = fmaxf(a.y, a.w);
+    b.area = mul_rn(sub_rn(b.ymax, b.ymin), sub_rn(b.xmax, b.xmin));
+    b.cls = cls;
+    return b;
+}
+// iou_above on pre-normalised boxes (same operations in the same order: bit-identical decisions)
+__device__ __forceinline__ bool iou_above_n(const NBox& i, const NBox& j, float thr) {
+    if (i.area <= 0.f || j.area <= 0.f) return false;
+    const float iy0 = fmaxf(i.ymin, j.ymin), ix0 = fmaxf(i.xmin, j.xmin);
+    const float iy1 = fminf(i.ymax, j.ymax), ix1 = fminf(i.xmax, j.xmax);
+    const float inter = mul_rn(fmaxf(sub_rn(iy1, iy0), 0.f), fmaxf(sub_rn(ix1, ix0), 0.f));
+    if (!(inter > 0.f)) return 0.f > thr;
+    const float uni = sub_rn(add_rn(i.area, j.area), inter);
+    const float q = __fdividef(inter, uni);
+    if (fabsf(q - thr) > 1e-5f) return q > thr;
+    return div_rn(inter, uni) > thr;
+}
+
+// bit (r, c) = c > r  &&  same class  &&  IoU(r, c) > thr   -- one ballot word per (row, 32 columns).  A CTA owns 256 rows x 32
+// columns: the row boxes are normalised once into shared memory (uniform reads in the loop), the column box lives in registers.
+__global__ void __launch_bounds__(256)
+nms_mask_kernel(const float4* s_box, const int32_t* s_cls, int n, int nwords, int pitch, float thr, unsigned* mask) {
+    __shared__ NBox rows[MASK_ROWS];
     const int w = blockIdx.x, pb = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row0 = blockIdx.y * MASK_ROWS;
     if (w * 32 + 31 <= row0) return;                              // word entirely at or below the diagonal
     const float4* bx = s_box + (size_t)pb * n;
     const int32_t* cl = s_cls + (size_t)pb * n;
+    {
+        const int r = row0 + threadIdx.x;
+        rows[threadIdx.x] = r < n ? norm_box(bx[r], cl[r]) : norm_box(make_float4(0.f, 0.f, 0.f, 0.f), -1);
+    }
     const int col = w * 32 + lane;
     const bool col_ok = col < n;
-    const float4 cb = col_ok ? bx[col] : make_float4(0.f, 0.f, 0.f, 0.f);
-    const int cc = col_ok ? cl[col] : -2;
-    unsigned* mp = mask + (size_t)pb * n * nwords;
-    for (int rr = warp; rr < MASK_ROWS; rr += 8) {
+    const NBox cb = col_ok ? norm_box(bx[col], cl[col]) : norm_box(make_float4(0.f, 0.f, 0.f, 0.f), -2);
+    unsigned* mp = mask + (size_t)pb * n * pitch;                 // rows padded to 16 B: the scan reads them with 128-bit loads
+    __syncthreads();
+    for (int rr = warp * 32; rr < warp * 32 + 32; ++rr) {
         const int r = row0 + rr;
         if (r >= n) break;
-        if (w * 32 + 31 <= r) continue;
-        const float4 rb = bx[r];                                  // uniform address: broadcast
-        const int rc = cl[r];
-        const bool bit = col_ok && col > r && cc == rc && rc >= 0 && iou_above(rb, cb, thr);
+        if (w * 32 + 31 <= r) break;                              // the remaining rows of this warp lie below the diagonal too
+        const NBox rb = rows[rr];                                 // uniform address: broadcast
+        const bool bit = col_ok && col > r && cb.cls == rb.cls && rb.cls >= 0 && iou_above_n(rb, cb, thr);
         const unsigned word = __ballot_sync(0xffffffffu, bit);
-        if (lane == 0) mp[(size_t)r * nwords + w] = word;
+        if (lane == 0) mp[(size_t)r * pitch + w] = word;
     }
 }
 
 // greedy selection over the bit matrix; one CTA (256 threads, thread t owns removed-word t) per problem.
-// The sweep is a latency chain (one dependent round per 32 candidates), so nothing on it may wait for global memory or for a
-// single thread's shared-memory round trips:
-//   * the mask rows of the candidates two blocks ahead are prefetched into a 3-deep shared-memory ring by warps 1-7
-//     (coalesced, 8 loads in flight per thread) while warp 0 resolves the current block;
-//   * warp 0 resolves a block with every lane holding one candidate (index, class, diagonal word) in registers and the
-//     32-step dependency chain running on warp shuffles (all lanes compute the same `cur` / `kept` / `total`);
-//   * per-class counters (tf NMS stops a class at max_output_size) live in shared memory and are only touched when class
-//     ids were given.
-constexpr int SCAN_RING = 3;
+// The sweep is a latency chain (one dependent round per 32 candidates), so nothing on it may wait for memory:
+//   * warp 0 resolves a block with lane b holding candidate b (index, class) and two mask words of its row, both loaded one block
+//     ahead: the DIAGONAL word (suppression inside the block) and the NEXT word (this block's effect on the next block, passed on in
+//     a register as `carry`), so the chain of the next block never waits for the removal words below;
+//   * with one class and no per-class cap every lane fetches the 32 diagonal words by (independent) shuffles and runs the same
+//     32-step chain on registers; with classes the chain walks the surviving candidates through shuffles and shared counters
+//     (tf NMS stops a class at max_output_size);
+//   * thread t > wi + 1 loads word t of the kept rows straight from global memory (no staging) into a small register buffer and ORs
+//     it into its removal word one round LATER: the L2 round trip overlaps the next block's chain (more than 8 kept rows in a block --
+//     the case that fills the output within a few blocks -- are ORed at once).
 __global__ void __launch_bounds__(256)
-nms_scan_kernel(const unsigned* mask, const int32_t* s_idx, const int32_t* s_cls, int n, int nwords,
+nms_scan_kernel(const unsigned* mask, const int32_t* s_idx, const int32_t* s_cls, int n, int nwords, int pitch,
                 int max_per_class, int max_total, int by_position, int single_class, int32_t* keep, int32_t* keep_count) {
-    extern __shared__ unsigned sh_rows[];                        // [SCAN_RING][32][nwords]
     __shared__ unsigned sh_cur, sh_kept;
     __shared__ int sh_total, sh_done;
     __shared__ int sh_cnt[MVF_MAX_CLASSES];
     const int pb = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const unsigned* mp = mask + (size_t)pb * n * nwords;
+    const unsigned* mp = mask + (size_t)pb * n * pitch;
     const int32_t* ip = s_idx + (size_t)pb * n;
     const int32_t* cp = s_cls + (size_t)pb * n;
     int32_t* kp = keep + (size_t)pb * max_total;
     for (int i = tid; i < MVF_MAX_CLASSES; i += blockDim.x) sh_cnt[i] = 0;
     if (tid == 0) { sh_total = 0; sh_done = 0; }
-    // rows blk*32 .. blk*32+31, words >= blk (upper triangle): warp `wfirst + k*wstride` copies row k..., lanes stride over the
-    // words of a row (coalesced), up to 8 loads in flight per lane before the stores; no integer divisions on this path
-    auto load_block = [&](int blk, int wfirst, int wstride) {
-        unsigned* dst = sh_rows + (size_t)(blk % SCAN_RING) * 32 * nwords;
-        for (int r = wfirst; r < 32; r += wstride) {
-            const int row = blk * 32 + r;
-            const unsigned* src = mp + (size_t)row * nwords;
-            for (int w0 = blk + lane; w0 < nwords; w0 += 8 * 32) {
-                unsigned v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { const int w = w0 + 32 * u; v[u] = (row < n && w < nwords) ? __ldg(src + w) : 0u; }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { const int w = w0 + 32 * u; if (w < nwords) dst[r * nwords + w] = v[u]; }
-            }
-        }
+    // warp 0: candidate `lane` of the next block -- index, class, diagonal word and next word of its mask row
+    int nidx = -1, ncls = -1;
+    unsigned ndiag = 0, nnext = 0;
+    auto prefetch = [&](int blk) {
+        const int row = blk * 32 + lane;
+        const bool ok = blk < nwords && row < n;
+        nidx = ok ? ip[row] : -1;
+        ncls = ok ? cp[row] : -1;
+        ndiag = ok ? __ldg(mp + (size_t)row * pitch + blk) : 0u;
+        nnext = (ok && blk + 1 < nwords) ? __ldg(mp + (size_t)row * pitch + blk + 1) : 0u;
     };
-    load_block(0, tid >> 5, 8);
-    if (nwords > 1) load_block(1, tid >> 5, 8);
-    int nidx = -1, ncls = -1;                                     // warp 0: candidate `lane` of the next block
-    if (tid < 32) { nidx = tid < n ? ip[tid] : -1; ncls = tid < n ? cp[tid] : -1; }
-    unsigned remv = 0;
+    if (tid < 32) prefetch(0);
+    unsigned remv = 0, carry = 0;
+    unsigned pend[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};          // words loaded in the previous round
     int total = 0;                                                // warp 0: running number of kept boxes (uniform)
     for (int wi = 0; wi < nwords; ++wi) {
-        if (tid == wi) sh_cur = remv;
-        __syncthreads();                                          // block wi is in shared memory, sh_cur published
-        const unsigned* rows = sh_rows + (size_t)(wi % SCAN_RING) * 32 * nwords;
-        if (tid >= 32) {
-            if (wi + 2 < nwords) load_block(wi + 2, (tid >> 5) - 1, 7);
-        } else {
+        if (tid == wi) sh_cur = remv;                             // contributions of the blocks before wi - 1
+        __syncthreads();
+        if (tid < 32) {
             const int idx = nidx, cls = ncls;
-            const unsigned diag = rows[lane * nwords + wi];
-            const int row = (wi + 1) * 32 + lane;                 // next block's candidates: issued now, used next iteration
-            nidx = (wi + 1 < nwords && row < n) ? ip[row] : -1;
-            ncls = (wi + 1 < nwords && row < n) ? cp[row] : -1;
-            unsigned cur = sh_cur, kept = 0;
+            const unsigned diag = ndiag, next = nnext;
+            prefetch(wi + 1);                                     // issued now, used next iteration
+            unsigned cur = sh_cur | carry, kept = 0;
             const unsigned present = __ballot_sync(0xffffffffu, idx >= 0);     // candidates of this block (a prefix of the lanes)
             int done = present != 0xffffffffu;                                 // a short block is the last one
-            unsigned alive = present & ~cur;                                   // visit only candidates that are not suppressed yet
+            if (single_class) {
+                unsigned dg[32];
+#pragma unroll
+                for (int b = 0; b < 32; ++b) dg[b] = __shfl_sync(0xffffffffu, diag, b);
+                int room = max_total - total;
+                cur |= ~present;                                               // absent candidates count as suppressed
+                if (room >= 32) {                                              // two dependent logic ops per candidate
+#pragma unroll
+                    for (int b = 0; b < 32; ++b)
+                        if (!((cur >> b) & 1u)) { kept |= 1u << b; cur |= dg[b]; }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 32; ++b)
+                        if (!((cur >> b) & 1u) && room > 0) { kept |= 1u << b; cur |= dg[b]; --room; }
+                }
+                if ((kept >> lane) & 1u) kp[total + __popc(kept & ((1u << lane) - 1u))] = by_position ? (wi * 32 + lane) : idx;
+                total += __popc(kept);
+            } else {
+                unsigned alive = present & ~cur;                               // visit only candidates that are not suppressed yet
 #pragma unroll 1
-            while (alive) {
-                if (total >= max_total) { done = 1; break; }                   // output full
-                const int b = __ffs(alive) - 1;
-                alive &= ~(1u << b);
-                if (!single_class) {
+                while (alive) {
+                    if (total >= max_total) { done = 1; break; }               // output full
+                    const int b = __ffs(alive) - 1;
+                    alive &= ~(1u << b);
                     const int c = __shfl_sync(0xffffffffu, cls, b);
                     const int cnt = sh_cnt[c];                                // broadcast read
                     if (cnt >= max_per_class) continue;                       // tf NMS stops a class at max_output_size
                     __syncwarp();
                     if (lane == 0) sh_cnt[c] = cnt + 1;
                     __syncwarp();
+                    const int bi = __shfl_sync(0xffffffffu, idx, b);
+                    if (lane == 0) kp[total] = by_position ? (wi * 32 + b) : bi;
+                    ++total;
+                    kept |= 1u << b;
+                    cur |= __shfl_sync(0xffffffffu, diag, b);
+                    alive &= ~cur;
                 }
-                const int bi = __shfl_sync(0xffffffffu, idx, b);
-                if (lane == 0) kp[total] = by_position ? (wi * 32 + b) : bi;
-                ++total;
-                kept |= 1u << b;
-                cur |= __shfl_sync(0xffffffffu, diag, b);
-                alive &= ~cur;
             }
+            carry = __reduce_or_sync(0xffffffffu, ((kept >> lane) & 1u) ? next : 0u);   // this block's suppression of block wi + 1
             if (total >= max_total) done = 1;
             if (lane == 0) { sh_total = total; sh_kept = kept; sh_done = done; }
         }
         __syncthreads();
         if (sh_done) break;
         unsigned kept = sh_kept;
-        if (tid > wi && tid < nwords) {
-            while (kept) {
-                const int b = __ffs(kept) - 1;
-                kept &= kept - 1;
-                remv |= rows[b * nwords + tid];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { remv |= pend[k]; pend[k] = 0u; }           // issued one round ago
+        if (tid > wi + 1 && tid < nwords) {                       // word wi + 1 travels in `carry`
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (kept) {
+                    const int b = __ffs(kept) - 1;
+                    kept &= kept - 1;
+                    pend[k] = __ldg(mp + (size_t)(wi * 32 + b) * pitch + tid);
+                }
+            }
+            if (kept) {                                           // many kept rows: independent predicated loads, one wait
+#pragma unroll 8
+                for (int b = 0; b < 32; ++b)
+                    if ((kept >> b) & 1u) remv |= __ldg(mp + (size_t)(wi * 32 + b) * pitch + tid);
             }
         }
     }
@@ -280,7 +345,7 @@ nms_scan_kernel(const unsigned* mask, const int32_t* s_idx, const int32_t* s_cls
     if (tid == 0 && keep_count) keep_count[pb] = ntotal;
 }
 
-struct NmsWs { u64* keys; int32_t* s_idx; float4* s_box; int32_t* s_cls; unsigned* mask; size_t bytes; };
+struct NmsWs { u64* keys; int32_t* rank; int32_t* s_idx; float4* s_box; int32_t* s_cls; unsigned* mask; size_t bytes; };
 
 static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -290,10 +355,11 @@ static NmsWs carve_nms(void* ws, int nprob, int n, int n_pad) {
     size_t off = 0;
     const int nwords = (n + 31) / 32;
     w.keys = (u64*)(p + off); off += align_up((size_t)nprob * n_pad * sizeof(u64));
+    w.rank = (int32_t*)(p + off); off += align_up((size_t)nprob * n * sizeof(int32_t));
     w.s_idx = (int32_t*)(p + off); off += align_up((size_t)nprob * n * sizeof(int32_t));
     w.s_box = (float4*)(p + off); off += align_up((size_t)nprob * n * sizeof(float4));
     w.s_cls = (int32_t*)(p + off); off += align_up((size_t)nprob * n * sizeof(int32_t));
-    w.mask = (unsigned*)(p + off); off += align_up((size_t)nprob * n * nwords * sizeof(unsigned));
+    w.mask = (unsigned*)(p + off); off += align_up((size_t)nprob * n * ((nwords + 3) & ~3) * sizeof(unsigned));
     w.bytes = off;
     return w;
 }
@@ -303,13 +369,11 @@ static int run_mask_scan(const NmsWs& w, int nprob, int n, float thr, int max_pe
                          int single_class, int32_t* keep, int32_t* keep_count, cudaStream_t s) {
     const int nwords = (n + 31) / 32;
     dim3 gm(nwords, (n + MASK_ROWS - 1) / MASK_ROWS, nprob);
-    nms_mask_kernel<<<gm, 256, 0, s>>>(w.s_box, w.s_cls, n, nwords, thr, w.mask);
+    const int pitch = (nwords + 3) & ~3;
+    nms_mask_kernel<<<gm, 256, 0, s>>>(w.s_box, w.s_cls, n, nwords, pitch, thr, w.mask);
     count_launch();
-    const size_t scan_smem = (size_t)SCAN_RING * 32 * nwords * sizeof(unsigned);   // 96 KB at the 8192-box limit
-    if (scan_smem > 32 * 1024 &&                     // static shared memory (class counters) counts against the 48 KB default
-        cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem) != cudaSuccess) return MVF_ECUDA;
-    nms_scan_kernel<<<nprob, 256, scan_smem, s>>>(w.mask, w.s_idx, w.s_cls, n, nwords, max_per_class, max_total, by_position,
-                                                   single_class, keep, keep_count);
+    nms_scan_kernel<<<nprob, 256, 0, s>>>(w.mask, w.s_idx, w.s_cls, n, nwords, pitch, max_per_class, max_total, by_position,
+                                          single_class, keep, keep_count);
     count_launch();
     return check_launch();
 }
@@ -317,11 +381,11 @@ static int run_mask_scan(const NmsWs& w, int nprob, int n, float thr, int max_pe
 // ---- refine_detections ---------------------------------------------------------------------------
 __global__ void refine_prepare_kernel(const float* rois, const float* probs, const float* deltas, const float* windows,
                                       float s0, float s1, float s2, float s3, int N, int K, float min_conf, int n_pad,
-                                      float4* refined, int32_t* cls_out, float* score_out, u64* keys) {
+                                      float4* refined, int32_t* cls_out, float* score_out, u64* keys, int32_t* rank) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (i >= n_pad) return;
-    if (i >= N) { keys[(size_t)b * n_pad + i] = KEY_EXCLUDED; return; }
+    if (i >= N) { keys[(size_t)b * n_pad + i] = excluded_key((unsigned)i); return; }
     const size_t o = (size_t)b * N + i;
     const float* pr = probs + o * K;
     int cls = 0; float best = pr[0];
@@ -335,7 +399,8 @@ __global__ void refine_prepare_kernel(const float* rois, const float* probs, con
     cls_out[o] = cls;
     score_out[o] = best;
     const bool cand = (cls > 0) && (min_conf == 0.f || best >= min_conf);                         // :1151-1157
-    keys[(size_t)b * n_pad + i] = cand ? make_key(best, (unsigned)i) : KEY_EXCLUDED;
+    keys[(size_t)b * n_pad + i] = cand ? make_key(best, (unsigned)i) : excluded_key((unsigned)i);
+    rank[o] = 0;
 }
 
 __global__ void write_detections_kernel(const int32_t* keep, const float4* refined, const int32_t* cls, const float* score,
@@ -407,13 +472,10 @@ extern "C" int mvf_nms(const float* boxes, const float* scores, const int32_t* c
     if (ws_bytes < w.bytes) return MVF_EWORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 gk((n_pad + 255) / 256, nprob);
-    nms_keys_kernel<<<gk, 256, 0, s>>>(scores, class_ids, w.keys, n, n_pad);
+    nms_keys_kernel<<<gk, 256, 0, s>>>(scores, class_ids, w.keys, w.rank, n, n_pad);
     count_launch();
-    int rc = sort_keys(w.keys, nprob, n_pad, s);
+    int rc = rank_scatter(w.keys, w.rank, (const float4*)boxes, class_ids, nprob, n, n_pad, w.s_idx, w.s_box, w.s_cls, s);
     if (rc != MVF_OK) return rc;
-    dim3 gg((n + 255) / 256, nprob);
-    nms_gather_kernel<<<gg, 256, 0, s>>>(w.keys, (const float4*)boxes, class_ids, n, n_pad, w.s_idx, w.s_box, w.s_cls);
-    count_launch();
     return run_mask_scan(w, nprob, n, iou_threshold, max_out, max_total, 0, class_ids == nullptr && max_out >= max_total, keep, keep_count, s);
 }
 
@@ -452,13 +514,10 @@ extern "C" int mvf_refine_detections(const float* rois, const float* probs, cons
     const int n_pad = next_pow2(N);
     dim3 gp((n_pad + 255) / 256, B);
     refine_prepare_kernel<<<gp, 256, 0, s>>>(rois, probs, deltas, windows, bbox_std[0], bbox_std[1], bbox_std[2], bbox_std[3],
-                                             N, K, min_confidence, n_pad, w.refined, w.cls, w.score, w.nms.keys);
+                                             N, K, min_confidence, n_pad, w.refined, w.cls, w.score, w.nms.keys, w.nms.rank);
     count_launch();
-    int rc = sort_keys(w.nms.keys, B, n_pad, s);
+    int rc = rank_scatter(w.nms.keys, w.nms.rank, w.refined, w.cls, B, N, n_pad, w.nms.s_idx, w.nms.s_box, w.nms.s_cls, s);
     if (rc != MVF_OK) return rc;
-    dim3 gg((N + 255) / 256, B);
-    nms_gather_kernel<<<gg, 256, 0, s>>>(w.nms.keys, w.refined, w.cls, N, n_pad, w.nms.s_idx, w.nms.s_box, w.nms.s_cls);
-    count_launch();
     // per-class NMS (<= max_inst per class, :1171-1174) and top-max_inst by score (:1197-1201) in one scan
     rc = run_mask_scan(w.nms, B, N, nms_threshold, max_inst, max_inst, 0, 0, w.keep, out_count, s);
     if (rc != MVF_OK) return rc;
