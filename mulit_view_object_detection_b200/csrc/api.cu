@@ -5,6 +5,11 @@
 namespace mvf {
 std::atomic<unsigned long long> g_launches{0};
 static size_t align_up256(size_t v) { return (v + 255) & ~(size_t)255; }
+int project_rays_strided(const float* grid, const float* Rview, int rview_stride, const float* Kmat, const MvfGrid* g, int B, int C,
+                         int img_h, int proj_h, int proj_w, int samples, float* out, void* stream);             // project.cu
+int project_collapse_strided(const float* grid, const float* Rview, int rview_stride, const float* Kmat, const MvfGrid* g, int B, int C,
+                             int img_h, int proj_h, int proj_w, int samples, int flags, const float* w, float bias, float bn_scale,
+                             float bn_shift, float* out, void* stream);                                           // project.cu
 }  // namespace mvf
 
 using namespace mvf;
@@ -27,7 +32,7 @@ extern "C" const char* mvf_version(void) { return "mvfusion 0.1.0 (sm_100a)"; }
 extern "C" unsigned long long mvf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 // device scratch layout of the host pipeline: feats | Rcam | Kmat | fused grid | ray slices
-struct HostWs { float *feats, *Rcam, *R0, *Kmat, *grid, *out; char* k1t; size_t k1t_scene, bytes; };
+struct HostWs { float *feats, *Rcam, *Kmat, *grid, *out; char* k1t; size_t k1t_scene, bytes; };
 
 static HostWs carve_host(void* ws, const MvfGrid* g, int B, int V, int fh, int fw, int C, int ph, int pw, int S) {
     HostWs w;
@@ -35,7 +40,6 @@ static HostWs carve_host(void* ws, const MvfGrid* g, int B, int V, int fh, int f
     size_t off = 0;
     w.feats = (float*)(p + off); off += align_up256((size_t)B * V * fh * fw * C * sizeof(float));
     w.Rcam = (float*)(p + off); off += align_up256((size_t)B * V * 12 * sizeof(float));
-    w.R0 = (float*)(p + off); off += align_up256((size_t)B * 12 * sizeof(float));
     w.Kmat = (float*)(p + off); off += align_up256((size_t)B * 9 * sizeof(float));
     w.grid = (float*)(p + off); off += align_up256((size_t)B * g->nvox * g->nvox * g->nvox_z * C * sizeof(float));
     w.out = (float*)(p + off); off += align_up256((size_t)B * S * ph * pw * C * sizeof(float));
@@ -135,9 +139,8 @@ static int host_pipeline(const float* h_feats, const float* h_Rcam, const float*
     MVF_TRY(cudaStreamWaitEvent(ax->sd, ax->start, 0));
     MVF_TRY(cudaMemcpyAsync(w.Rcam, h_Rcam, (size_t)B * V * 12 * sizeof(float), cudaMemcpyHostToDevice, ax->sh));
     MVF_TRY(cudaMemcpyAsync(w.Kmat, h_Kmat, (size_t)B * 9 * sizeof(float), cudaMemcpyHostToDevice, ax->sh));
-    // proj_grid reads the main-view poses as a contiguous [B,3,4] tensor (Rcam[:,0], model_multi.py:245)
-    MVF_TRY(cudaMemcpy2DAsync(w.R0, 12 * sizeof(float), w.Rcam, (size_t)V * 12 * sizeof(float), 12 * sizeof(float), B,
-                              cudaMemcpyDeviceToDevice, ax->sh));
+    // (proj_grid projects into view 0, Rcam[:,0], model_multi.py:245: K3 reads those poses in place with the scene stride V*12 --
+    //  a strided 2-D device copy into a dense [B,3,4] measured 0.1-0.2 ms here, as much as K3 itself)
     MVF_TRY(cudaEventRecord(ax->ev_in[kMaxChunks], ax->sh));
     MVF_TRY(cudaStreamWaitEvent(ax->sc, ax->ev_in[kMaxChunks], 0));
     const int per = (B + kMaxChunks - 1) / kMaxChunks;          // scenes per chunk (1 unless B > 32)
@@ -162,12 +165,12 @@ static int host_pipeline(const float* h_feats, const float* h_Rcam, const float*
                                     d_bn_scale, d_bn_shift, w.grid + b0 * grid_scene, nullptr, nullptr, nullptr, ax->sc);
         if (rc != MVF_OK) return fail(rc);
         if (col)
-            rc = mvf_project_depth_collapse(w.grid + b0 * grid_scene, w.R0 + (size_t)b0 * 12, nullptr, w.Kmat + (size_t)b0 * 9, nullptr, g,
-                                            nb, C, img_h, proj_h, proj_w, samples, MVF_FLAG_RELU_OUT, 0.0, 0, MVF_WHOLE_GRID,
-                                            col->d_w, col->bias, col->bn_scale, col->bn_shift, w.out + b0 * out_scene, ax->sc);
+            rc = project_collapse_strided(w.grid + b0 * grid_scene, w.Rcam + (size_t)b0 * V * 12, V * 12, w.Kmat + (size_t)b0 * 9, g,
+                                          nb, C, img_h, proj_h, proj_w, samples, MVF_FLAG_RELU_OUT,
+                                          col->d_w, col->bias, col->bn_scale, col->bn_shift, w.out + b0 * out_scene, ax->sc);
         else
-            rc = mvf_project_rays(w.grid + b0 * grid_scene, w.R0 + (size_t)b0 * 12, nullptr, w.Kmat + (size_t)b0 * 9, nullptr, g,
-                                  nb, C, img_h, proj_h, proj_w, samples, 0, 0.0, 0, MVF_WHOLE_GRID, w.out + b0 * out_scene, nullptr, nullptr, ax->sc);
+            rc = project_rays_strided(w.grid + b0 * grid_scene, w.Rcam + (size_t)b0 * V * 12, V * 12, w.Kmat + (size_t)b0 * 9, g,
+                                      nb, C, img_h, proj_h, proj_w, samples, w.out + b0 * out_scene, ax->sc);
         if (rc != MVF_OK) return fail(rc);
         MVF_TRY(cudaEventRecord(ax->ev[chunk], ax->sc));
         MVF_TRY(cudaStreamWaitEvent(ax->sd, ax->ev[chunk], 0));

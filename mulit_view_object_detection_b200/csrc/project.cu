@@ -21,6 +21,7 @@ struct ProjParams {
     const float* w;                     // [S] depth-collapse weights (device) or null
     float* out; int32_t* out_vox; uint8_t* out_valid;
     int B, C, ph, pw, S, X, Y, Z, x_begin, Xs, flags;
+    int rv_stride;                      // floats between two scenes' view poses (12: a dense [B,3,4]; V*12: view 0 of Rcam [B,V,3,4])
     float r, lo[3], hi[3], n[3];
     float bias, bn_scale, bn_shift;
     float zs[MVF_MAX_SAMPLES];
@@ -37,7 +38,7 @@ __device__ __forceinline__ void build_scene(const ProjParams& p, int b, SceneXf*
     const float* K = p.Kmat + (size_t)b * 9;
 #pragma unroll
     for (int e = 0; e < 9; ++e) xf->Kp[e] = mul_rn(K[e], p.r);
-    const float* A = p.Rview + (size_t)b * 12;
+    const float* A = p.Rview + (size_t)b * p.rv_stride;
 #pragma unroll
     for (int e = 0; e < 12; ++e) xf->A[e] = A[e];
     const float* P0 = p.Rmain ? p.Rmain + (size_t)b * 12 : A;
@@ -222,13 +223,31 @@ static int fill_proj_params(ProjParams& p, const float* grid, const float* Rview
         p.hi[0] = p.hi[1] = (float)g->vmax; p.hi[2] = (float)g->vmax_z;
     }
     p.n[0] = p.n[1] = (float)(g->nvox * 1.0); p.n[2] = (float)(g->nvox_z * 1.0);   // :296
-    p.bias = 0.f; p.bn_scale = 1.f; p.bn_shift = 0.f;
+    p.bias = 0.f; p.bn_scale = 1.f; p.bn_shift = 0.f; p.rv_stride = 12;
     return MVF_OK;
 }
 
 }  // namespace mvf
 
 using namespace mvf;
+
+// rview_stride: floats between two scenes' poses in Rview -- the pipelines of api.cu project into view 0 of Rcam [B,V,3,4] in place
+// (stride V*12) instead of gathering the main-view poses into a dense [B,3,4] first.
+namespace mvf {
+int project_rays_strided(const float* grid, const float* Rview, int rview_stride, const float* Kmat, const MvfGrid* g, int B, int C,
+                         int img_h, int proj_h, int proj_w, int samples, float* out, void* stream) {
+    ProjParams p;
+    int rc = fill_proj_params(p, grid, Rview, nullptr, Kmat, nullptr, g, B, C, img_h, proj_h, proj_w, samples, 0, 0.0, 0, MVF_WHOLE_GRID);
+    if (rc != MVF_OK) return rc;
+    if (!out) return MVF_ENULL;
+    if (!aligned16(out)) return MVF_EALIGN;
+    p.out = out; p.rv_stride = rview_stride;
+    dim3 grd((samples * proj_h * proj_w + K3_THREADS - 1) / K3_THREADS, B);
+    project_rays_kernel<<<grd, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+    count_launch();
+    return check_launch();
+}
+}  // namespace mvf
 
 extern "C" int mvf_project_rays(const float* grid, const float* Rview, const float* Rmain, const float* Kmat,
                                 const float* grid_pos, const MvfGrid* g, int B, int C, int img_h,
@@ -249,6 +268,21 @@ extern "C" int mvf_project_rays(const float* grid, const float* Rview, const flo
     return check_launch();
 }
 
+static int collapse_launch(ProjParams& p, int B, int C, int proj_h, int proj_w, const float* w, float bias, float bn_scale,
+                           float bn_shift, float* out, void* stream);
+
+namespace mvf {
+int project_collapse_strided(const float* grid, const float* Rview, int rview_stride, const float* Kmat, const MvfGrid* g, int B, int C,
+                             int img_h, int proj_h, int proj_w, int samples, int flags, const float* w, float bias, float bn_scale,
+                             float bn_shift, float* out, void* stream) {
+    ProjParams p;
+    int rc = fill_proj_params(p, grid, Rview, nullptr, Kmat, nullptr, g, B, C, img_h, proj_h, proj_w, samples, flags, 0.0, 0, MVF_WHOLE_GRID);
+    if (rc != MVF_OK) return rc;
+    p.rv_stride = rview_stride;
+    return collapse_launch(p, B, C, proj_h, proj_w, w, bias, bn_scale, bn_shift, out, stream);
+}
+}  // namespace mvf
+
 extern "C" int mvf_project_depth_collapse(const float* grid, const float* Rview, const float* Rmain,
                                           const float* Kmat, const float* grid_pos, const MvfGrid* g,
                                           int B, int C, int img_h, int proj_h, int proj_w, int samples,
@@ -259,6 +293,11 @@ extern "C" int mvf_project_depth_collapse(const float* grid, const float* Rview,
     int rc = fill_proj_params(p, grid, Rview, Rmain, Kmat, grid_pos, g, B, C, img_h, proj_h, proj_w, samples, flags,
                               grid_dist, x_begin, x_count);
     if (rc != MVF_OK) return rc;
+    return collapse_launch(p, B, C, proj_h, proj_w, w, bias, bn_scale, bn_shift, out, stream);
+}
+
+static int collapse_launch(ProjParams& p, int B, int C, int proj_h, int proj_w, const float* w, float bias, float bn_scale,
+                           float bn_shift, float* out, void* stream) {
     if (!out || !w) return MVF_ENULL;
     if (!aligned16(out)) return MVF_EALIGN;
     p.out = out; p.w = w; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
