@@ -295,6 +295,65 @@ def c2_line(dev, peak):
             "refine_detections_1000x25_ms": timed(lambda: m.refine_detections_graph(det[0], det[1], det[2], window, cfg))}
 
 
+def c4_line(dev, scenes=8, views=5, steps=3):
+    """Config c4: full model_multi Mask R-CNN inference (model.py: MaskRCNN.predict), ResNet-101 + FPN backbone, 5 views per scene,
+    batch 8 scenes on one GPU, 640x640 inputs, 256-channel pyramid, GRID_REAS='add', the reference InferenceConfig's 40^3 grid
+    (samples/interior/interior_multi.py:397-421), random-init weights.  The fusion neck, ProposalLayer, PyramidROIAlign and
+    DetectionLayer run on this repo's kernels; backbone / RPN / head convolutions are cuDNN / cuBLAS fp32 (TF32 off), timed a
+    second time with TF32 allowed.  Inputs resident in HBM; the per-stage times come from CUDA events around each stage."""
+    import torch
+    import mulit_view_object_detection_b200 as m
+    from mulit_view_object_detection_b200 import synthetic as syn
+    cfg = m.FusionConfig(IMAGE_SHAPE=np.array([640, 640, 3]), NUM_VIEWS=views, IMAGES_PER_GPU=scenes, TOP_DOWN_PYRAMID_SIZE=256,
+                         NUM_CLASSES=23, nvox=40, nvox_z=40, samples=20, GRID_REAS="add", BACKBONE="resnet101",
+                         DETECTION_MIN_CONFIDENCE=0.0)
+    out = {"workload": "c4: MaskRCNN.predict, ResNet-101 + FPN, %d scenes x %d views, 640x640, 256-ch pyramid, 40^3 grid, GRID_REAS=add, "
+                       "1000 proposals, 100 detections + masks, random-init weights, inputs in HBM" % (scenes, views)}
+    with torch.no_grad():
+        net = m.MaskRCNN("inference", cfg, device=dev, seed=4)
+        rng = np.random.default_rng(4000)
+        images = torch.from_numpy(rng.normal(0, 50, (scenes, views, 640, 640, 3)).astype(np.float32)).to(dev)
+        _, Rcam, Kmat = syn.make_scene(cfg, scenes, views, 8, 8, 4, seed=4001)
+        meta = np.stack([m.weights_io.compose_image_meta(0, (640, 640, 3), (640, 640, 3), (0, 0, 640, 640), 1.0,
+                                                         np.zeros(cfg.NUM_CLASSES, np.int32)) for _ in range(scenes)]).astype(np.float32)
+        a = net.get_anchors((640, 640, 3))
+        anchors = torch.from_numpy(np.broadcast_to(a, (scenes,) + a.shape).copy()).to(dev)
+        inputs = [images, meta, anchors, torch.from_numpy(Rcam).to(dev), torch.from_numpy(Kmat).to(dev)]
+        for tf32 in (False, True):
+            net.allow_tf32 = tf32
+            for _ in range(2):
+                res = net.predict(inputs)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = m.launch_count()
+            e0.record()
+            for _ in range(steps):
+                res = net.predict(inputs)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            key = "tf32_dense" if tf32 else "fp32_dense"
+            out[key] = {"ms_per_batch": ms, "scenes_per_s": scenes / ms * 1e3, "views_per_s": scenes * views / ms * 1e3}
+            if not tf32:
+                out["library_kernel_launches_per_batch"] = (m.launch_count() - n0) // steps
+                out["detections_checksum"] = float(res[0].double().sum())
+                out["n_detections"] = int((res[0][..., 4] > 0).sum())
+        # stage split (fp32): backbone+FPN | fusion neck | RPN + proposals | heads
+        net.allow_tf32 = False
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        P = net.build_resnet_fpn(images)
+        ev[1].record()
+        maps = m.fusion_neck(P, inputs[3], inputs[4], cfg, params=net.neck_params)
+        ev[2].record()
+        torch.cuda.synchronize()
+        out["stage_ms_fp32"] = {"backbone_fpn": ev[0].elapsed_time(ev[1]), "fusion_neck_levels_4_5_6": ev[1].elapsed_time(ev[2]),
+                                "rpn_proposals_heads": out["fp32_dense"]["ms_per_batch"] - ev[0].elapsed_time(ev[2])}
+        del net, images, P, maps, res
+    torch.cuda.empty_cache()
+    return out
+
+
 def cooperative_lines(dev, world, rank):
     """The cooperative (strong-scaling) splits BASELINE.json names, measured at EVERY --gpus N so that the driver's SCALE record
     carries them: all ranks work on the SAME scenes and the timed step includes the NCCL exchange.
@@ -576,6 +635,11 @@ def run_b200(args):
         if world == 1 and not args.no_convlstm:
             line["k2_convlstm"] = convlstm_line(dev, local)
             line["c2_heads"] = c2_line(dev, peak)
+            if not args.no_model:
+                try:
+                    line["c4_model"] = c4_line(dev)
+                except Exception as e:                       # the headline line must not depend on the extra
+                    line["c4_model"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1 and not args.no_cpu_baseline:
             n_cpu = 24
             v, s_per, threads = cpu_reference_run(1, 16, n_cpu, 1)
@@ -672,6 +736,7 @@ def main():
     ap.add_argument("--scenes", type=int, default=16, help="scenes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-convlstm", action="store_true", help="skip the extra K2 (ConvLSTM on tensor cores) measurement")
+    ap.add_argument("--no-model", action="store_true", help="skip the extra c4 (full model_multi inference) measurement")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-cooperative", action="store_true", help="skip the cooperative multi-GPU splits (c3 / c5 strong scaling)")
     ap.add_argument("--strategy", default="scene", choices=["scene", "view_allreduce", "view_reduce_scatter", "slab_owner", "slab_owner_scatter", "lstm_slab"],

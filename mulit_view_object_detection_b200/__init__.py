@@ -24,7 +24,7 @@ _LAYER_NAMES = (
     "channel_mean", "HostPipeline", "set_weights", "weights", "reused_lay",
 )
 
-__all__ = ["FusionConfig", "LIB_PATH", *_LIB_NAMES, *_LAYER_NAMES]
+__all__ = ["FusionConfig", "LIB_PATH", "MaskRCNN", *_LIB_NAMES, *_LAYER_NAMES]
 
 
 def __getattr__(name):
@@ -33,6 +33,8 @@ def __getattr__(name):
         return getattr(importlib.import_module("._lib", __name__), name)
     if name in _LAYER_NAMES:
         return getattr(importlib.import_module(".layers", __name__), name)
-    if name in ("_lib", "layers", "dist", "weights_io", "synthetic", "config"):
+    if name == "MaskRCNN":
+        return importlib.import_module(".model", __name__).MaskRCNN
+    if name in ("_lib", "layers", "dist", "weights_io", "synthetic", "config", "model", "model_host"):
         return importlib.import_module("." + name, __name__)
     raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -45,3 +45,4 @@ from .projection import proj_grid, depth_sampling, project_indices
 from .roi_align import pyramid_roi_align, roi_levels, crop_and_resize
 from .detection import (apply_box_deltas, clip_boxes, iou_tf, non_max_suppression,
                         refine_detections, detection_layer, proposal_layer, norm_boxes)
+from . import model

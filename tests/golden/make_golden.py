@@ -389,7 +389,199 @@ def gen_depth_sampling():
         save("depth_sampling_" + mode, x=x, out=arr(out), S=np.int32(S), F=np.int32(F), **_flat(LAYER_WEIGHTS))
 
 
+# ---- the dense graphs of the full model (mrcnn/model_multi.py:497-641 backbone + FPN, :1265-1306 RPN, :1335-1444 heads) --
+# SURVEY.md section 8(f) rank 4.  Again the reference's OWN graph builders are executed; the Keras layers they instantiate
+# are functional stand-ins evaluated in float64 on the CPU (torch), weights looked up by the reference's layer names.  That
+# pins the wiring the product's model.py has to reproduce: strides and padding placement, block order, shortcut placement,
+# the top-down additions, P6, the (h, w, anchor) order of the RPN reshapes, the FC-as-convolution flattening order, the
+# transposed-convolution kernel layout.  The weights are model_host.init_params + randomize (seeded); the fixture stores
+# their checksum, the inputs and the outputs.
+def _t64(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(arr(x), dtype=np.float64))
+
+
+def _same_pads(n, k, s):
+    out = -(-n // s)
+    total = max((out - 1) * s + k - n, 0)
+    return total // 2, total - total // 2
+
+
+def _act(y, kind):
+    if kind in (None, "linear"):
+        return y
+    if kind == "relu":
+        return np.maximum(y, 0)
+    if kind == "sigmoid":
+        return 1.0 / (1.0 + np.exp(-y))
+    if kind == "softmax":
+        e = np.exp(y - y.max(axis=-1, keepdims=True))
+        return e / e.sum(axis=-1, keepdims=True)
+    raise AssertionError(kind)
+
+
+class _MConv2D:
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding="valid", activation=None, use_bias=True, name=None, **k):
+        self.filters, self.name, self.padding, self.activation = filters, name, padding.lower(), activation
+        self.strides = (strides, strides) if isinstance(strides, int) else tuple(strides)
+        self.kernel_size = tuple(kernel_size)
+
+    def __call__(self, x, name=None):
+        import torch.nn.functional as F_
+        W, b = LAYER_WEIGHTS[name or self.name]
+        assert W.shape[:2] == self.kernel_size and W.shape[-1] == self.filters, (name or self.name, W.shape)
+        t = _t64(x).permute(0, 3, 1, 2)
+        if self.padding == "same":
+            (pt, pb), (pl, pr) = _same_pads(t.shape[2], W.shape[0], self.strides[0]), _same_pads(t.shape[3], W.shape[1], self.strides[1])
+            t = F_.pad(t, (pl, pr, pt, pb))
+        y = F_.conv2d(t, _t64(W).permute(3, 2, 0, 1), _t64(b), stride=self.strides)
+        return T(_act(y.permute(0, 2, 3, 1).numpy(), self.activation).astype(np.float32))
+
+
+class _MConv2DTranspose(_MConv2D):
+    def __call__(self, x, name=None):
+        import torch.nn.functional as F_
+        W, b = LAYER_WEIGHTS[name or self.name]                      # keras: [kh, kw, out, in]
+        assert self.padding == "valid" and W.shape[2] == self.filters
+        y = F_.conv_transpose2d(_t64(x).permute(0, 3, 1, 2), _t64(W).permute(3, 2, 0, 1), _t64(b), stride=self.strides)
+        return T(_act(y.permute(0, 2, 3, 1).numpy(), self.activation).astype(np.float32))
+
+
+class _MDense:
+    def __init__(self, units, activation=None, name=None, **k):
+        self.units, self.activation, self.name = units, activation, name
+
+    def __call__(self, x, name=None):
+        W, b = LAYER_WEIGHTS[name or self.name]
+        assert W.shape[-1] == self.units
+        return T(_act(arr(x).astype(np.float64) @ W.astype(np.float64) + b.astype(np.float64), self.activation).astype(np.float32))
+
+
+class _MActivation:
+    def __init__(self, kind, name=None, **k):
+        self.kind = kind
+
+    def __call__(self, x, name=None):
+        return T(_act(arr(x).astype(np.float64), self.kind).astype(np.float32))
+
+
+class _MZeroPadding2D:
+    def __init__(self, padding, **k):
+        self.p = padding
+
+    def __call__(self, x, name=None):
+        (a, b) = self.p
+        return T(np.pad(arr(x), ((0, 0), (a, a), (b, b), (0, 0))))
+
+
+class _MMaxPool2D:
+    def __init__(self, pool_size=(2, 2), strides=None, padding="valid", **k):
+        self.k = tuple(pool_size)
+        self.s = (strides, strides) if isinstance(strides, int) else tuple(strides)
+        self.padding = padding.lower()
+
+    def __call__(self, x, name=None):
+        import torch.nn.functional as F_
+        t = _t64(x).permute(0, 3, 1, 2)
+        if self.padding == "same":
+            (pt, pb), (pl, pr) = _same_pads(t.shape[2], self.k[0], self.s[0]), _same_pads(t.shape[3], self.k[1], self.s[1])
+            t = F_.pad(t, (pl, pr, pt, pb), value=float("-inf"))
+        return T(F_.max_pool2d(t, self.k, self.s).permute(0, 2, 3, 1).numpy().astype(np.float32))
+
+
+class _MUpSampling2D:
+    def __init__(self, size=(2, 2), **k):
+        self.size = tuple(size)
+
+    def __call__(self, x, name=None):
+        return T(np.repeat(np.repeat(arr(x), self.size[0], axis=1), self.size[1], axis=2))
+
+
+class _MAdd:
+    def __init__(self, **k):
+        pass
+
+    def __call__(self, xs):
+        return T(arr(xs[0]) + arr(xs[1]))
+
+
+class _MReshape:
+    def __init__(self, shape, name=None, **k):
+        self.shape = tuple(int(v) for v in shape)
+
+    def __call__(self, x):
+        return T(arr(x).reshape((arr(x).shape[0],) + self.shape))
+
+
+class _MTimeDistributed:
+    def __init__(self, layer, name=None, **k):
+        self.layer, self.name = layer, name
+
+    def __call__(self, x, training=None):
+        a = arr(x)
+        if isinstance(self.layer, mm.BatchNorm):
+            assert training is False or training is None
+            scale, shift = oracle.batch_norm_affine(*LAYER_WEIGHTS[self.name])
+            return T(a * scale + shift)
+        flat = T(a.reshape((a.shape[0] * a.shape[1],) + a.shape[2:]))
+        y = arr(self.layer(flat, name=self.name))
+        return T(y.reshape(a.shape[:2] + y.shape[1:]))
+
+
+def _install_model_layers():
+    KL = mm.KL
+    KL.Lambda, KL.Activation, KL.TimeDistributed, KL.Conv2D, KL.Conv2DTranspose = _Lambda, _MActivation, _MTimeDistributed, _MConv2D, _MConv2DTranspose
+    KL.Dense, KL.ZeroPadding2D, KL.MaxPool2D, KL.UpSampling2D, KL.Add, KL.Reshape = _MDense, _MZeroPadding2D, _MMaxPool2D, _MUpSampling2D, _MAdd, _MReshape
+    mm.PyramidROIAlign.__call__ = lambda self, inputs: self.call(inputs)       # keras.engine.Layer.__call__ -> call (in memory only)
+    mm.K.squeeze = lambda x, axis: T(np.squeeze(arr(x), axis))
+    mm.K.int_shape = lambda x: tuple(int(v) for v in arr(x).shape)
+
+
+def gen_model_graphs():
+    from mulit_view_object_detection_b200 import model_host as MH
+    _install_model_layers()
+    cfg = FusionConfig(IMAGE_SHAPE=np.array([64, 64, 3]), NUM_VIEWS=2, IMAGES_PER_GPU=1, TOP_DOWN_PYRAMID_SIZE=16, NUM_CLASSES=5,
+                       BACKBONE="resnet50", POOL_SIZE=3, MASK_POOL_SIZE=4, FPN_CLASSIF_FC_LAYERS_SIZE=32)
+    cfg.TRAIN_BN = False
+    params = MH.randomize(MH.init_params(cfg, seed=5), seed=6)
+    LAYER_WEIGHTS.clear()
+    LAYER_WEIGHTS.update(MH.named_weights(params))
+    rng = np.random.default_rng(7)
+    images = rng.normal(0, 40, (1, 2, 64, 64, 3)).astype(np.float32)
+    P = quiet(mm.build_resnet_fpn, T(images), cfg)
+    P = [arr(p) for p in P]
+    rpn = [arr(a) for a in quiet(mm.rpn_graph, T(P[1][:, 0]), 3, 1)]
+    maps = [rng.standard_normal((1, 64 // s, 64 // s, 16)).astype(np.float32) for s in (4, 8, 16, 32)]
+    rois = syn.make_rois(rng, 1, 12, pad_frac=0.1)
+    meta = MH_meta(cfg)
+    cls = [arr(a) for a in quiet(mm.fpn_classifier_graph, T(rois), [T(m) for m in maps], T(meta), cfg.POOL_SIZE, cfg.NUM_CLASSES,
+                                 train_bn=False, fc_layers_size=cfg.FPN_CLASSIF_FC_LAYERS_SIZE)]
+    mask = arr(quiet(mm.build_fpn_mask_graph, T(rois[:, :6]), [T(m) for m in maps], T(meta), cfg.MASK_POOL_SIZE, cfg.NUM_CLASSES,
+                     train_bn=False))
+    # the reference's pure-NumPy host helpers, run unmodified (mrcnn/utils.py:842-900, :1112-1143; model_multi.py:89-103)
+    cfg.BACKBONE_STRIDES, cfg.COMPUTE_BACKBONE_SHAPE = [4, 8, 16, 32, 64], None
+    shapes = mm.compute_backbone_shapes(cfg, (128, 192, 3))
+    anchors = ref_utils.generate_pyramid_anchors((32, 64, 128, 256, 512), [0.5, 1, 2], shapes, [4, 8, 16, 32, 64], 1)
+    save("model_graphs", images=images, **{"P%d" % (i + 2): p for i, p in enumerate(P)},
+         rpn_logits=rpn[0], rpn_probs=rpn[1], rpn_bbox=rpn[2],
+         **{"map%d" % i: m for i, m in enumerate(maps)}, rois=rois, meta=meta,
+         cls_logits=cls[0], cls_probs=cls[1], cls_bbox=cls[2], mask=mask,
+         weights_checksum=np.float64(MH.checksum(params)),
+         backbone_shapes=shapes, anchors=anchors.astype(np.float64), anchors_norm=ref_utils.norm_boxes(anchors, (128, 192)),
+         denorm=ref_utils.denorm_boxes(ref_utils.norm_boxes(anchors[:64], (128, 192)), (128, 192)))
+
+
+def MH_meta(cfg):
+    h, w = int(cfg.IMAGE_SHAPE[0]), int(cfg.IMAGE_SHAPE[1])
+    return mm.compose_image_meta(0, (h, w, 3), (h, w, 3), (0, 0, h, w), 1.0, np.zeros([cfg.NUM_CLASSES], dtype=np.int32))[None].astype(np.float32)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                      # python make_golden.py gen_model_graphs ...: only the named generators
+        for g in sys.argv[1:]:
+            globals()[g]()
+        sys.exit(0)
+    gen_model_graphs()
     gen_grid_reas()
     gen_depth_sampling()
     gen_unproject_project()
