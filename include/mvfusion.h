@@ -317,6 +317,22 @@ int mvf_unproject_fuse_project_host(const float* h_feats, const float* h_Rcam, c
                                     int proj_h, int proj_w, int samples,
                                     float* h_out, void* dev_ws, size_t dev_ws_bytes, MvfHostAux* aux, void* stream);
 
+/* ---- the fused pipeline on DEVICE buffers ----------------------------------------------------
+ * replaces unproj_feat -> grid_reas(sum|mean|max [+BN+ReLU]) -> proj_grid (model_multi.py:130-228, :401-404, :231-322) for a
+ * batch of scenes resident in device memory: feats [B,V,fh,fw,C], Rcam [B,V,3,4], Kmat [B,3,3] in, fused grid [B,X,Y,Z,C] and
+ * ray slices [B,S,ph,pw,C] out -- the same kernels and bits as mvf_unproject_fuse(_tc) followed by mvf_project_rays(Rcam[:,0]).
+ * For the configurations mvf_unproject_fuse_tc_supported() accepts, the feature split, the tensor-core unprojection and the
+ * projection are queued on `stream` with programmatic stream serialization and overlap scene by scene (per-scene progress
+ * counters in the workspace).  Asynchronous; `stream` is ordered as usual for whatever the caller queues next.
+ * ws: mvf_unproject_fuse_project_workspace_bytes(...) bytes of device scratch (may be NULL when the tensor-core path does not apply). */
+size_t mvf_unproject_fuse_project_workspace_bytes(int B, int V, int fh, int fw, int C);
+int mvf_unproject_fuse_project(const float* feats, const float* Rcam, const float* Kmat,
+                               const MvfGrid* g, int B, int V, int fh, int fw, int C,
+                               int img_h, int img_w, int mode, int flags,
+                               const float* bn_scale, const float* bn_shift,
+                               int proj_h, int proj_w, int samples,
+                               float* grid_out, float* rays_out, void* ws, size_t ws_bytes, void* stream);
+
 /* One pyramid level of the fusion neck (model_multi.py:2382-2404) from HOST buffers: as above, with depth_sampling (non-conv3d
  * branch, :481-487) fused into the projection, so h_out is PG [B,ph,pw,C] and only features go in / PG comes out.
  * d_depth_w [S] device; depth_bias / depth_bn_scale / depth_bn_shift: the folded scalars of the depth conv and its BatchNorm.

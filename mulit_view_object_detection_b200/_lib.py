@@ -86,6 +86,9 @@ _SIGS = {
     "mvf_host_aux_destroy": (_i, [_p]),
     "mvf_unproject_fuse_project_host": (_i, [_p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p,
                                              _i, _i, _i, _p, _p, _sz, _p, _p]),
+    "mvf_unproject_fuse_project_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "mvf_unproject_fuse_project": (_i, [_p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p,
+                                        _i, _i, _i, _p, _p, _p, _sz, _p]),
     "mvf_fusion_neck_level_host": (_i, [_p, _p, _p, _G, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p,
                                         _i, _i, _i, _p, _f, _f, _f, _p, _p, _sz, _p, _p]),
     "mvf_error_string": (C.c_char_p, [_i]),

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <stdio.h>
 #include <atomic>
+#include <utility>
 #include "mvfusion.h"
 
 namespace mvf {
@@ -14,6 +15,20 @@ namespace mvf {
 extern std::atomic<unsigned long long> g_launches;
 
 inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream is still running (as soon
+// as every CTA of the predecessor has executed griddepcontrol.launch_dependents or exited).  Kernels launched this way must not rely on
+// the predecessor's memory being flushed: they synchronise through device counters (unproject_tc.cu).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 inline int check_launch() {
     cudaError_t e = cudaGetLastError();

@@ -713,11 +713,45 @@ def proj_grid_depth_sampling(inputs, config, proj_size, name, params=None, view=
 
 def unproject_fuse_project(feats, Rcam, Kmat, config, proj_size, mode="sum", bn=None, relu_out=False,
                            grid_out=None, out=None, tensor_cores=None):
-    """The fused pipeline: unproj_feat -> grid_reas(sum|mean|max [+BN+ReLU]) -> proj_grid.
-    Two launches (K1 or K1T, K3); returns (ray slices [B,S,P,P,C], fused grid [B,X,Y,Z,C])."""
-    fused = unproject_fuse(feats, Rcam, Kmat, config, mode=mode, bn=bn, relu_out=relu_out, out=grid_out, tensor_cores=tensor_cores)
-    rays = proj_grid([fused, Rcam, Kmat], config, proj_size, out=out)
-    return rays, fused
+    """The fused pipeline: unproj_feat -> grid_reas(sum|mean|max [+BN+ReLU]) -> proj_grid; returns (ray slices [B,S,P,P,C],
+    fused grid [B,X,Y,Z,C]).  One C call (``mvf_unproject_fuse_project``): for the configurations K1T accepts, the feature split,
+    the tensor-core unprojection and the projection are queued with programmatic stream serialization and overlap scene by scene
+    (same kernels, same bits as ``unproject_fuse`` followed by ``proj_grid``); otherwise slot kernel, then projection.
+    ``tensor_cores=False`` forces the two plain calls on the slot kernel."""
+    if tensor_cores is False:
+        fused = unproject_fuse(feats, Rcam, Kmat, config, mode=mode, bn=bn, relu_out=relu_out, out=grid_out, tensor_cores=False)
+        return proj_grid([fused, Rcam, Kmat], config, proj_size, out=out), fused
+    feats, Rcam, Kmat = _cuda(feats, "feats"), _cuda(Rcam, "Rcam"), _cuda(Kmat, "Kmat")
+    if feats.dim() != 5 or Rcam.dim() != 4 or Kmat.dim() != 3:
+        raise ValueError("expected feats [B,V,fh,fw,C], Rcam [B,V,3,4], Kmat [B,3,3]")
+    B, V, fh, fw, Cc = feats.shape
+    if tuple(Rcam.shape) != (B, V, 3, 4) or tuple(Kmat.shape) != (B, 3, 3):
+        raise ValueError("Rcam %s / Kmat %s do not match feats %s" % (tuple(Rcam.shape), tuple(Kmat.shape), tuple(feats.shape)))
+    g = grid_from_config(config)
+    ph, pw = _as_hw(proj_size)
+    S = int(config.samples)
+    m = _FUSE[mode]
+    if m == _lib.FUSE_NONE:
+        raise ValueError("unproject_fuse_project needs a view reduction (sum | mean | max)")
+    gshape, rshape = (B, g.nvox, g.nvox, g.nvox_z, Cc), (B, S, ph, pw, Cc)
+    if grid_out is None:
+        grid_out = torch.empty(gshape, dtype=torch.float32, device=feats.device)
+    elif tuple(grid_out.shape) != gshape or not grid_out.is_contiguous():
+        raise ValueError("grid_out must be a contiguous %s tensor" % (gshape,))
+    if out is None:
+        out = torch.empty(rshape, dtype=torch.float32, device=feats.device)
+    elif tuple(out.shape) != rshape or not out.is_contiguous():
+        raise ValueError("out must be a contiguous %s tensor" % (rshape,))
+    scale, shift = _bn_affine(bn, Cc, feats.device)
+    flags = _lib.FLAG_RELU_OUT if relu_out else 0
+    if tensor_cores and not lib.mvf_unproject_fuse_tc_supported(V, Cc, m, flags):
+        raise ValueError("the tensor-core unprojection needs mode sum/mean, C % 64 == 0 and C <= 256")
+    ws = _k1t_workspace(feats.device, lib.mvf_unproject_fuse_project_workspace_bytes(B, V, fh, fw, Cc))
+    ih, iw = _image_hw(config)
+    rc = lib.mvf_unproject_fuse_project(_ptr(feats), _ptr(Rcam), _ptr(Kmat), C.byref(g), B, V, fh, fw, Cc, ih, iw, m, flags,
+                                        _ptr(scale), _ptr(shift), ph, pw, S, _ptr(grid_out), _ptr(out), _ptr(ws), ws.numel(), _stream())
+    check(rc, "mvf_unproject_fuse_project")
+    return out, grid_out
 
 
 def unproject_unet_fuse(feats, Rcam, Kmat, scope, config, params):

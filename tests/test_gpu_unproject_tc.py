@@ -93,7 +93,7 @@ def test_k1t_workload_T_against_slot_kernel_and_dispatch():
     d = to_dev(feats, Rcam, Kmat)
     n0 = m.launch_count()
     auto = m.unproject_fuse(*d, cfg, mode="sum")
-    assert m.launch_count() - n0 == 3
+    assert m.launch_count() - n0 == 2          # split kernel + tensor-core kernel
     tc = m.unproject_fuse(*d, cfg, mode="sum", tensor_cores=True)
     assert torch.equal(auto, tc)                                        # deterministic: same bits run to run
     slot = m.unproject_fuse(*d, cfg, mode="sum", tensor_cores=False)
