@@ -321,9 +321,8 @@ int mvf_unproject_fuse_project_host(const float* h_feats, const float* h_Rcam, c
  * replaces unproj_feat -> grid_reas(sum|mean|max [+BN+ReLU]) -> proj_grid (model_multi.py:130-228, :401-404, :231-322) for a
  * batch of scenes resident in device memory: feats [B,V,fh,fw,C], Rcam [B,V,3,4], Kmat [B,3,3] in, fused grid [B,X,Y,Z,C] and
  * ray slices [B,S,ph,pw,C] out -- the same kernels and bits as mvf_unproject_fuse(_tc) followed by mvf_project_rays(Rcam[:,0]).
- * For the configurations mvf_unproject_fuse_tc_supported() accepts, the feature split, the tensor-core unprojection and the
- * projection are queued on `stream` with programmatic stream serialization and overlap scene by scene (per-scene progress
- * counters in the workspace).  Asynchronous; `stream` is ordered as usual for whatever the caller queues next.
+ * One call instead of two plus the gather of the main-view poses; for the configurations mvf_unproject_fuse_tc_supported()
+ * accepts, the feature split runs under the tensor-core unprojection (as in mvf_unproject_fuse_tc).  Asynchronous.
  * ws: mvf_unproject_fuse_project_workspace_bytes(...) bytes of device scratch (may be NULL when the tensor-core path does not apply). */
 size_t mvf_unproject_fuse_project_workspace_bytes(int B, int V, int fh, int fw, int C);
 int mvf_unproject_fuse_project(const float* feats, const float* Rcam, const float* Kmat,

@@ -6,13 +6,10 @@ namespace mvf {
 std::atomic<unsigned long long> g_launches{0};
 static size_t align_up256(size_t v) { return (v + 255) & ~(size_t)255; }
 int project_rays_strided(const float* grid, const float* Rview, int rview_stride, const float* Kmat, const MvfGrid* g, int B, int C,
-                         int img_h, int proj_h, int proj_w, int samples, float* out, void* stream,
-                         const unsigned* done, unsigned done_target, const unsigned* go, unsigned gen);       // project.cu
-int project_follow_prepare();                                                                                    // project.cu
+                         int img_h, int proj_h, int proj_w, int samples, float* out, void* stream);             // project.cu
 int k1t_launch(const float* feats, const float* Rcam, const float* Rmain, const float* Kmat, const MvfGrid* g, int B, int V, int fh, int fw,
                int C, int img_h, int img_w, int mode, int flags, double grid_dist, int x_begin, int x_count, const float* bn_scale,
-               const float* bn_shift, float* out, void* ws, size_t ws_bytes, void* stream, unsigned** done_out, unsigned* done_target,
-               const unsigned** go_out, unsigned* gen_out);                                                     // unproject_tc.cu
+               const float* bn_shift, float* out, void* ws, size_t ws_bytes, void* stream);                                     // unproject_tc.cu
 int project_collapse_strided(const float* grid, const float* Rview, int rview_stride, const float* Kmat, const MvfGrid* g, int B, int C,
                              int img_h, int proj_h, int proj_w, int samples, int flags, const float* w, float bias, float bn_scale,
                              float bn_shift, float* out, void* stream);                                           // project.cu
@@ -176,7 +173,7 @@ static int host_pipeline(const float* h_feats, const float* h_Rcam, const float*
                                           col->d_w, col->bias, col->bn_scale, col->bn_shift, w.out + b0 * out_scene, ax->sc);
         else
             rc = project_rays_strided(w.grid + b0 * grid_scene, w.Rcam + (size_t)b0 * V * 12, V * 12, w.Kmat + (size_t)b0 * 9, g,
-                                      nb, C, img_h, proj_h, proj_w, samples, w.out + b0 * out_scene, ax->sc, nullptr, 0, nullptr, 0);
+                                      nb, C, img_h, proj_h, proj_w, samples, w.out + b0 * out_scene, ax->sc);
         if (rc != MVF_OK) return fail(rc);
         MVF_TRY(cudaEventRecord(ax->ev[chunk], ax->sc));
         MVF_TRY(cudaStreamWaitEvent(ax->sd, ax->ev[chunk], 0));
@@ -202,11 +199,11 @@ extern "C" int mvf_unproject_fuse_project_host(const float* h_feats, const float
                          proj_h, proj_w, samples, nullptr, h_out, dev_ws, dev_ws_bytes, aux, stream);
 }
 
-// ---- the fused pipeline on DEVICE buffers, one stream, three overlapping kernels ------------------------------------------
-// unproject_tc_kernel is bound by shared-memory bandwidth and leaves ~2/3 of the HBM bandwidth idle; its feature split and the
-// projection are pure HBM streams.  All three are queued on `stream` with programmatic stream serialization and synchronise
-// through per-scene counters in the workspace: the split of scene b+1 and the projection of scene b-1 run UNDER the tensor-core
-// kernel's work on scene b.  No side streams, no events; same kernels and bits as the two plain calls.
+// ---- the fused pipeline on DEVICE buffers: one call, one stream ----------------------------------------------------------------
+// unproj_feat -> grid_reas -> proj_grid for a batch of scenes: K1T with its feature split running under it (unproject_tc.cu), or the
+// slot kernel for the modes K1T does not take, then K3 reading the main-view poses in place.  (Measured and not shipped in round 2:
+// K3 as a programmatic dependent that follows the tensor-core kernel scene by scene through per-scene store counters -- correct, but
+// the projection's loads and stores on the same SMs slowed unproject_tc_kernel by about as much as they hid: DESIGN.md section 3.1b.)
 extern "C" size_t mvf_unproject_fuse_project_workspace_bytes(int B, int V, int fh, int fw, int C) {
     return mvf_unproject_fuse_tc_workspace_bytes(B, V, fh, fw, C);
 }
@@ -222,24 +219,17 @@ extern "C" int mvf_unproject_fuse_project(const float* feats, const float* Rcam,
     if (mode < MVF_FUSE_SUM || mode > MVF_FUSE_MAX) return MVF_EINVAL;
     if (flags & MVF_FLAG_WORLD_GRID) return MVF_EUNSUPPORTED;      // (the notebook variant's projection needs grid_pos: use the two calls)
     int rc;
-    unsigned* done = nullptr;
-    const unsigned* go = nullptr;
-    unsigned done_target = 0, gen = 0;
     if (mvf_unproject_fuse_tc_supported(V, C, mode, flags)) {
         if (!ws) return MVF_ENULL;
-        if ((rc = project_follow_prepare()) != MVF_OK) return rc;
         rc = k1t_launch(feats, Rcam, nullptr, Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, 0.0, 0, MVF_WHOLE_GRID,
-                        bn_scale, bn_shift, grid_out, ws, ws_bytes, stream, &done, &done_target, &go, &gen);
+                        bn_scale, bn_shift, grid_out, ws, ws_bytes, stream);
     } else {                                                       // CUDA-core slot kernel, then the projection as an ordinary launch
         rc = mvf_unproject_fuse(feats, Rcam, nullptr, Kmat, g, B, V, fh, fw, C, img_h, img_w, mode, flags, 0.0, 0, MVF_WHOLE_GRID,
                                 bn_scale, bn_shift, grid_out, nullptr, nullptr, nullptr, stream);
     }
     if (rc != MVF_OK) return rc;
     // proj_grid projects into view 0 (Rcam[:,0], model_multi.py:245): read in place with the scene stride V*12
-#ifdef MVF_K1T_EXP_PLAINK3
-    done = nullptr;                                                // EXPERIMENT: the projection as an ordinary launch behind the (triggering) unprojection
-#endif
-    return project_rays_strided(grid_out, Rcam, V * 12, Kmat, g, B, C, img_h, proj_h, proj_w, samples, rays_out, stream, done, done_target, go, gen);
+    return project_rays_strided(grid_out, Rcam, V * 12, Kmat, g, B, C, img_h, proj_h, proj_w, samples, rays_out, stream);
 }
 
 // One pyramid level of the fusion neck (model_multi.py:2382-2404) from HOST buffers: unproj_feat -> grid_reas(sum|mean|max

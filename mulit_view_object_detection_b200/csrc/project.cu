@@ -21,8 +21,6 @@ struct ProjParams {
     const float* w;                     // [S] depth-collapse weights (device) or null
     float* out; int32_t* out_vox; uint8_t* out_valid;
     int B, C, ph, pw, S, X, Y, Z, x_begin, Xs, flags;
-    const unsigned* go; unsigned gen;             // generation token of the producing call (unproject_tc.cu, K1tParams::go)
-    const unsigned* done; unsigned done_target;   // non-null: per-scene progress counter of the kernel that is still WRITING the grid (see project_rays_kernel)
     int rv_stride;                      // floats between two scenes' view poses (12: a dense [B,3,4]; V*12: view 0 of Rcam [B,V,3,4])
     float r, lo[3], hi[3], n[3];
     float bias, bn_scale, bn_shift;
@@ -86,11 +84,6 @@ __device__ __forceinline__ long long slab_offset(const ProjParams& p, int b, con
     return ((((long long)b * p.Xs + xs) * p.Y + id[1]) * p.Z + id[2]) * p.C;
 }
 
-// FOLLOW: the kernel was launched with programmatic stream serialization behind the unprojection that is still writing the grid
-// (unproject_tc_kernel, TMA stores): the CTAs of scene b wait until that kernel has reported all of scene b's stores complete
-// (p.done[b] >= p.done_target, acquire) and read the grid with L2-coherent loads -- the read-only path must not be used on memory
-// that changes while the kernel runs.  CTAs are dispatched scene by scene in the order the producer finishes them.
-template <bool FOLLOW>
 __global__ void __launch_bounds__(K3_THREADS)
 project_rays_kernel(const __grid_constant__ ProjParams p) {
     __shared__ SceneXf xf;
@@ -113,56 +106,8 @@ project_rays_kernel(const __grid_constant__ ProjParams p) {
         if (p.out_vox) { p.out_vox[o * 3 + 0] = id[0]; p.out_vox[o * 3 + 1] = id[1]; p.out_vox[o * 3 + 2] = id[2]; }
         if (p.out_valid) p.out_valid[o] = (uint8_t)valid;
     }
-    if (FOLLOW) {                                                  // (the index work above overlaps the producer)
-        if (threadIdx.x == 0) {
-            unsigned v;
-            for (long long spin = 0; p.go; ++spin) {               // the producing call's counters are valid once its token is up
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.go) : "memory");
-                if (v == p.gen) break;
-                __nanosleep(200);
-                if (spin > (1ll << 25)) __trap();
-            }
-            for (long long spin = 0;; ++spin) {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.done + b) : "memory");
-                if (v >= p.done_target) break;
-                __nanosleep(200);
-                if (spin > (1ll << 25)) __trap();                  // a lost producer traps instead of hanging the GPU
-            }
-        }
-        __syncthreads();
-    }
     const int t0 = t - lane;
     const int C4 = p.C >> 2;
-    if (FOLLOW && C4 <= 64) {
-        // next to the producer only one or two of these CTAs fit on an SM: four samples (eight 16-byte loads per lane) in flight per warp
-        // instead of one keep the memory pipe full at that occupancy
-        for (int j0 = 0; j0 < 32; j0 += 4) {
-            if (t0 + j0 >= per_scene) break;                          // warp-uniform
-            float4 v[4][2];
-            long long sj[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                sj[u] = __shfl_sync(FULL, src, j0 + u);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c4 = lane + 32 * h;
-                    v[u][h] = (sj[u] >= 0 && c4 < C4) ? __ldcg(reinterpret_cast<const float4*>(p.grid + sj[u] + 4 * c4)) : zero4();
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int tj = t0 + j0 + u;
-                if (tj >= per_scene) break;
-                float* o = p.out + ((size_t)b * per_scene + tj) * p.C;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c4 = lane + 32 * h;
-                    if (c4 < C4) stcs4(o + 4 * c4, v[u][h]);
-                }
-            }
-        }
-        return;
-    }
     for (int jj = 0; jj < 32; ++jj) {
         const long long sj = __shfl_sync(FULL, src, jj);
         const int tj = t0 + jj;
@@ -171,7 +116,7 @@ project_rays_kernel(const __grid_constant__ ProjParams p) {
         if (sj >= 0) {
             const float* g = p.grid + sj;
             for (int c4 = lane; c4 < C4; c4 += 32)
-                stcs4(o + 4 * c4, FOLLOW ? __ldcg(reinterpret_cast<const float4*>(g + 4 * c4)) : ldg4(g + 4 * c4));
+                stcs4(o + 4 * c4, ldg4(g + 4 * c4));
         } else {
             for (int c4 = lane; c4 < C4; c4 += 32) stcs4(o + 4 * c4, zero4());
         }
@@ -279,7 +224,7 @@ static int fill_proj_params(ProjParams& p, const float* grid, const float* Rview
         p.hi[0] = p.hi[1] = (float)g->vmax; p.hi[2] = (float)g->vmax_z;
     }
     p.n[0] = p.n[1] = (float)(g->nvox * 1.0); p.n[2] = (float)(g->nvox_z * 1.0);   // :296
-    p.bias = 0.f; p.bn_scale = 1.f; p.bn_shift = 0.f; p.rv_stride = 12; p.done = nullptr; p.done_target = 0; p.go = nullptr; p.gen = 0;
+    p.bias = 0.f; p.bn_scale = 1.f; p.bn_shift = 0.f; p.rv_stride = 12;
     return MVF_OK;
 }
 
@@ -290,28 +235,16 @@ using namespace mvf;
 // rview_stride: floats between two scenes' poses in Rview -- the pipelines of api.cu project into view 0 of Rcam [B,V,3,4] in place
 // (stride V*12) instead of gathering the main-view poses into a dense [B,3,4] first.
 namespace mvf {
-// Loads project_rays_kernel<true> and gives it the carve-out of the producer it runs next to; to be called BEFORE that producer is
-// launched (see k1t_launch in unproject_tc.cu for both reasons).
-int project_follow_prepare() {
-    return cudaFuncSetAttribute(project_rays_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) == cudaSuccess
-               ? MVF_OK : MVF_ECUDA;
-}
-
 int project_rays_strided(const float* grid, const float* Rview, int rview_stride, const float* Kmat, const MvfGrid* g, int B, int C,
-                         int img_h, int proj_h, int proj_w, int samples, float* out, void* stream,
-                         const unsigned* done, unsigned done_target, const unsigned* go, unsigned gen) {
+                         int img_h, int proj_h, int proj_w, int samples, float* out, void* stream) {
     ProjParams p;
     int rc = fill_proj_params(p, grid, Rview, nullptr, Kmat, nullptr, g, B, C, img_h, proj_h, proj_w, samples, 0, 0.0, 0, MVF_WHOLE_GRID);
     if (rc != MVF_OK) return rc;
     if (!out) return MVF_ENULL;
     if (!aligned16(out)) return MVF_EALIGN;
-    p.out = out; p.rv_stride = rview_stride; p.done = done; p.done_target = done_target; p.go = go; p.gen = gen;
+    p.out = out; p.rv_stride = rview_stride;
     dim3 grd((samples * proj_h * proj_w + K3_THREADS - 1) / K3_THREADS, B);
-    if (done) {
-        if (launch_pdl(project_rays_kernel<true>, grd, dim3(K3_THREADS), 0, (cudaStream_t)stream, p) != cudaSuccess) return MVF_ECUDA;
-    } else {
-        project_rays_kernel<false><<<grd, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
-    }
+    project_rays_kernel<<<grd, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
     count_launch();
     return check_launch();
 }
@@ -331,7 +264,7 @@ extern "C" int mvf_project_rays(const float* grid, const float* Rview, const flo
     p.out = out; p.out_vox = out_vox; p.out_valid = out_valid;
     const int per_scene = samples * proj_h * proj_w;
     dim3 grd((per_scene + K3_THREADS - 1) / K3_THREADS, B);
-    project_rays_kernel<false><<<grd, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
+    project_rays_kernel<<<grd, K3_THREADS, 0, (cudaStream_t)stream>>>(p);
     count_launch();
     return check_launch();
 }

@@ -1,8 +1,10 @@
-"""GPU parity of the device-resident fused pipeline (``mvf_unproject_fuse_project``): the feature split, the tensor-core
-unprojection and the projection overlap scene by scene through programmatic dependent launch and per-scene device counters, and
-must return the SAME BITS as the plain calls they are made of (unproject_fuse, proj_grid: model_multi.py:130-228, :401-404,
-:231-322) and, through them, the oracle's values.  Also: the standalone K1T call (its split now runs under it), repeated calls
-on the shared workspace, one-scene batches, slot-kernel modes, BN + ReLU, and workload T at 16 scenes."""
+"""GPU parity of the device-resident fused pipeline (``mvf_unproject_fuse_project``) and of the cross-kernel overlap inside K1T:
+the feature split runs as its own persistent kernel UNDER the tensor-core unprojection (programmatic dependent launch, per-scene
+device counters, a per-call generation token).  Results must be the SAME BITS as the plain calls (unproject_fuse, proj_grid:
+model_multi.py:130-228, :401-404, :231-322) whatever else is in flight on the stream -- the failures this guards against only
+showed when older kernels were still running at enqueue time and the previous call had used another batch size -- and,
+through them, the oracle's values.  Also: repeated calls on the shared workspace, one-scene batches, slot-kernel modes, BN + ReLU,
+workload T at 16 scenes."""
 import numpy as np
 import pytest
 
@@ -90,3 +92,38 @@ def test_fused_workload_T_16_scenes():
         r1 = m.proj_grid([g1, one[1], one[2]], cfg, P)
         assert torch.equal(grid[b:b + 1], g1), b
         assert torch.equal(rays[b:b + 1], r1), b
+
+
+def test_overlap_with_busy_stream_and_changing_batch_sizes():
+    """The sequences that exposed the round-2 races: a kernel still running when the call is enqueued (no host sync), after a call
+    with another batch size (other workspace layout, other tensor maps).  Every result must match the slot kernel."""
+    import torch
+    m = _m()
+    B, V, Cc, P = 16, 8, 256, 40
+    cfg = _cfg(64, V, samples=20, image=640)
+    feats, Rcam, Kmat = scene(cfg, B, V, 40, 40, Cc, seed=1000)
+    d = to_dev(feats, Rcam, Kmat)
+    slot = m.unproject_fuse(*d, cfg, mode="sum", tensor_cores=False)
+    one = [t[0:1].contiguous() for t in d]
+    grid = torch.zeros((B, 64, 64, 64, Cc), device="cuda")
+    rays = torch.zeros((B, 20, P, P, Cc), device="cuda")
+
+    def bad(g):
+        torch.cuda.synchronize()
+        return int(((g - slot).abs() > (1e-5 * slot.abs() + 1e-6)).sum())
+
+    for rep in range(2):
+        m.unproject_fuse(*one, cfg, mode="sum"); torch.cuda.synchronize()
+        grid.fill_(-3.0)                                   # still running when the next call is enqueued
+        m.unproject_fuse_project(*d, cfg, P, grid_out=grid, out=rays)
+        assert bad(grid) == 0
+        assert torch.equal(rays, m.proj_grid([grid, d[1], d[2]], cfg, P))
+        m.unproject_fuse(*one, cfg, mode="sum"); torch.cuda.synchronize()
+        rays.fill_(0.0)
+        m.unproject_fuse(*d, cfg, mode="sum", out=grid)
+        assert bad(grid) == 0
+        m.unproject_fuse_project(*d, cfg, P, grid_out=grid, out=rays)
+        grid.fill_(-3.0)
+        m.unproject_fuse_project(*d, cfg, P, grid_out=grid, out=rays)
+        c = grid.clone()                                   # consumer enqueued right behind the call
+        assert bad(c) == 0
