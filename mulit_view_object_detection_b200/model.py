@@ -111,7 +111,9 @@ class MaskRCNN:
     def set_params(self, params):
         self.params = params
         self.dense = _Dense(params, self.device)
-        self.neck_params = {k: v for k, v in params.items() if k.startswith("grid_reas")}
+        # the neck's learnables once as device tensors / folded BatchNorm affines (layers.prepare_params)
+        neck = {k: v for k, v in params.items() if k.startswith("grid_reas")}
+        self.neck_params = L.prepare_params(neck, self.device) if self.device.type == "cuda" else neck
 
     def load_weights(self, filepath, by_name=True, exclude=None):
         """``load_weights`` (model_multi.py:2592-2642): Keras layers restored BY NAME from ``{layer: get_weights() list}`` --
@@ -310,7 +312,7 @@ class MaskRCNN:
             windows.append(win[0])
         molded = np.stack(molded)
         image_shape = molded.shape[2:]
-        anchors = np.ascontiguousarray(np.broadcast_to(self.get_anchors(image_shape), (cfg.BATCH_SIZE,) + self.get_anchors(image_shape).shape))
+        anchors = np.broadcast_to(self.get_anchors(image_shape), (cfg.BATCH_SIZE,) + self.get_anchors(image_shape).shape).copy()
         detections, _, _, mrcnn_mask, _, _, _ = self.predict([molded, np.stack(metas), anchors, Rcam, Kmat])
         detections, mrcnn_mask = detections.cpu().numpy(), mrcnn_mask.cpu().numpy()
         results = []

@@ -184,12 +184,42 @@ def init_params(config, seed=0):
         P["mrcnn_mask_conv%d" % i], P["mrcnn_mask_bn%d" % i] = _conv_p(rng, 3, 3, D if i == 1 else 128, 128), _bn_p(128)
     P["mrcnn_mask_deconv"] = {"kernel": _glorot(rng, (2, 2, 128, 128), 4 * 128, 4 * 128), "bias": np.zeros(128, np.float32)}
     P["mrcnn_mask"] = _conv_p(rng, 1, 1, 128, K)
-    # fusion neck, GRID_REAS='add' (the other modes take their learnables from the caller / weights_io.fusion_params_from_keras)
-    S = int(config.samples)
-    for lvl in (2, 3, 4, 5, 6):
-        P["grid_reas_P%d" % lvl] = _bn_p(D)
-        P["grid_reas_depth_PG%d" % lvl] = {"weight": _glorot(rng, (S,), S, 1), "bias": 0.0, "bn": (1.0, 0.0, 0.0, 1.0)}
+    P.update(init_neck_params(config, rng))
     return P
+
+
+def init_neck_params(config, rng):
+    """Learnables of the fusion neck for ``config.GRID_REAS`` in the format ``layers.fusion_neck`` / ``weights_io.fusion_params_from_keras``
+    use (model_multi.py:394-488): add / mean / max -> BatchNorm; ident -> 1x1x1 conv over the V*C concatenated views; lstm3d ->
+    ConvLSTM kernel [3,3,3,C+F,4F]; conv3d -> the four U-Net convolutions + the two depthwise / 1x1 pairs of depth_sampling."""
+    D, S, V = int(config.TOP_DOWN_PYRAMID_SIZE), int(config.samples), int(config.NUM_VIEWS)
+    mode = getattr(config, "GRID_REAS", "add")
+    ident_bn = lambda c: (np.ones(c, np.float32), np.zeros(c, np.float32), np.zeros(c, np.float32), np.ones(c, np.float32))
+    out = {}
+    for lvl in (2, 3, 4, 5, 6):
+        if mode in ("add", "mean", "max"):
+            g = {"bn": ident_bn(D)}
+        elif mode == "ident":
+            g = {"weight": _glorot(rng, (V * D, D), V * D, D), "bias": np.zeros(D, np.float32), "bn": ident_bn(D)}
+        elif mode == "lstm3d":
+            g = {"W": _glorot(rng, (3, 3, 3, 2 * D, 4 * D), 27 * 2 * D, 27 * 4 * D), "b": np.zeros(4 * D, np.float32), "bn": ident_bn(D)}
+        elif mode == "conv3d":
+            def c3(cin, cout, transposed=False):                    # Conv3DTranspose kernels are [3,3,3,out,in]
+                shape = (3, 3, 3, cout, cin) if transposed else (3, 3, 3, cin, cout)
+                return {"W": _glorot(rng, shape, 27 * cin, 27 * cout), "b": np.zeros(cout, np.float32), "bn": ident_bn(cout)}
+            g = {"conv1": c3(V * D, 2 * D), "conv2": c3(2 * D, 4 * D), "deconv1": c3(4 * D, 2 * D, True), "deconv2": c3(4 * D, D, True)}
+        else:
+            raise ValueError("GRID_REAS=%r" % (mode,))
+        out["grid_reas_P%d" % lvl] = g
+        if mode == "conv3d":
+            out["grid_reas_depth_PG%d" % lvl] = {
+                "dw1": {"w": np.ones(D * S, np.float32), "b": np.zeros(D * S, np.float32)},
+                "conv1": {"W": _glorot(rng, (D * S, 512), D * S, 512), "b": np.zeros(512, np.float32), "bn": ident_bn(512)},
+                "dw2": {"w": np.ones(512, np.float32), "b": np.zeros(512, np.float32)},
+                "conv2": {"W": _glorot(rng, (512, D), 512, D), "b": np.zeros(D, np.float32), "bn": ident_bn(D)}}
+        else:
+            out["grid_reas_depth_PG%d" % lvl] = {"weight": _glorot(rng, (S,), S, 1), "bias": 0.0, "bn": (1.0, 0.0, 0.0, 1.0)}
+    return out
 
 
 def randomize(params, seed=1):
@@ -199,9 +229,21 @@ def randomize(params, seed=1):
     out = {}
     for name, p in params.items():
         p = dict(p)
-        if name.startswith("grid_reas_depth"):
+        if name.startswith("grid_reas_depth") and "weight" in p:
             p["bias"] = float(rng.normal(0, 0.05))
             p["bn"] = (float(rng.uniform(0.8, 1.2)), float(rng.normal(0, 0.05)), float(rng.normal(0, 0.05)), float(rng.uniform(0.7, 1.3)))
+        elif name.startswith("grid_reas") and any(isinstance(v, dict) for v in p.values()):
+            for k, q in p.items():                                  # conv3d neck: {'conv1': {'W','b','bn'}, ..., 'dw1': {'w','b'}}
+                q = dict(q)
+                if "bn" in q:
+                    c = np.asarray(q["bn"][0]).size
+                    q["bn"] = (rng.uniform(0.8, 1.2, c).astype(np.float32), rng.normal(0, 0.05, c).astype(np.float32),
+                               rng.normal(0, 0.05, c).astype(np.float32), rng.uniform(0.7, 1.3, c).astype(np.float32))
+                if "b" in q:
+                    q["b"] = rng.normal(0, 0.05, np.asarray(q["b"]).shape).astype(np.float32)
+                if "w" in q:
+                    q["w"] = rng.uniform(0.8, 1.2, np.asarray(q["w"]).shape).astype(np.float32)
+                p[k] = q
         elif "bn" in p:
             c = np.asarray(p["bn"][0]).size
             p["bn"] = (rng.uniform(0.8, 1.2, c).astype(np.float32), rng.normal(0, 0.05, c).astype(np.float32),
@@ -226,10 +268,18 @@ def named_weights(params):
 def checksum(params):
     """Order-independent float64 checksum of a parameter dictionary (fixtures store it to detect a drifting initialiser)."""
     tot = 0.0
+    def leaves(v):
+        if isinstance(v, dict):
+            for k in sorted(v):
+                yield from leaves(v[k])
+        elif isinstance(v, (tuple, list)):
+            for a in v:
+                yield from leaves(a)
+        else:
+            yield v
     for name in sorted(params):
         for key in sorted(params[name]):
-            v = params[name][key]
-            for a in (v if isinstance(v, (tuple, list)) else [v]):
+            for a in leaves(params[name][key]):
                 a = np.asarray(a, dtype=np.float64)
                 tot += float(np.sum(a * np.cos(np.arange(a.size, dtype=np.float64).reshape(a.shape))))
     return tot

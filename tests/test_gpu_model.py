@@ -107,3 +107,38 @@ def test_detect_end_to_end():
     assert (r["class_ids"] > 0).all() and r["masks"].dtype == bool
     again = net.detect(scenes, Rcam, Kmat)[0]
     assert np.array_equal(again["rois"], r["rois"]) and np.array_equal(again["masks"], r["masks"])           # deterministic
+
+
+@pytest.mark.parametrize("mode", ["conv3d", "ident", "lstm3d"])
+def test_model_neck_modes_vs_oracle(mode):
+    """The shipped configs use GRID_REAS='conv3d' (samples/interior/interior_multi.py:391,419): the model's fusion neck in the
+    tensor-core modes against oracle.fusion_neck fed the PRODUCT's pyramid (tolerance of the 3 x fp16 split: rtol 1e-5 plus 1e-5 of
+    the map's maximum), and the stages behind it on identical inputs as in the 'add' test."""
+    import mulit_view_object_detection_b200 as m
+    B, V = 1, 2
+    cfg = small_model_cfg(B, V)
+    cfg.GRID_REAS = mode
+    params = small_params(cfg, 31)
+    net = m.MaskRCNN("inference", cfg, params=params)
+    rng = np.random.default_rng(33)
+    images = rng.normal(0, 50, (B, V, 128, 128, 3)).astype(np.float32)
+    _, Rcam, Kmat = syn.make_scene(cfg, B, V, 8, 8, 4, seed=34, image_hw=(128, 128))
+    meta = np.stack([m.weights_io.compose_image_meta(0, (128, 128, 3), (128, 128, 3), (0, 0, 128, 128), 1.0,
+                                                     np.zeros(cfg.NUM_CLASSES, np.int32)) for _ in range(B)]).astype(np.float32)
+    a = net.get_anchors((128, 128, 3))
+    anchors = np.broadcast_to(a, (B,) + a.shape).copy()
+    res, feats = net.predict([images, meta, anchors, Rcam, Kmat], return_features=True)
+    det, mclass, mbbox, mmask, rois, rclass, rbbox = (t.cpu().numpy() for t in res)
+    P = [p.cpu().numpy() for p in feats["P"]]
+    maps = [p.cpu().numpy() for p in feats["maps"]]
+    o_maps = oracle.fusion_neck(P, Rcam, Kmat, cfg, params)
+    for lvl, (g, o) in enumerate(zip(maps, o_maps)):
+        assert g.shape == o.shape
+        np.testing.assert_allclose(g, o, rtol=1e-5, atol=1e-5 * max(1.0, float(np.abs(o).max())), err_msg="PG%d" % (lvl + 2))
+    assert maps[2].any() and not maps[0].any()
+    given = {"P": P, "maps": maps, "rpn_class": rclass, "rpn_bbox": rbbox, "rpn_rois": rois, "mrcnn_class": mclass, "mrcnn_bbox": mbbox,
+             "detections": det}
+    o = oracle.model.predict(images, meta, anchors, Rcam, Kmat, params, cfg, given=given)
+    np.testing.assert_allclose(rois, o["rpn_rois"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(det, o["detections"], rtol=0, atol=1e-6)
+    assert rel(mmask, o["mrcnn_mask"]) <= 2e-4
