@@ -295,7 +295,7 @@ def c2_line(dev, peak):
             "refine_detections_1000x25_ms": timed(lambda: m.refine_detections_graph(det[0], det[1], det[2], window, cfg))}
 
 
-def c4_line(dev, scenes=8, views=5, steps=3):
+def c4_line(dev, scenes=8, views=5, steps=3, grid_reas="add", channels=256):
     """Config c4: full model_multi Mask R-CNN inference (model.py: MaskRCNN.predict), ResNet-101 + FPN backbone, 5 views per scene,
     batch 8 scenes on one GPU, 640x640 inputs, 256-channel pyramid, GRID_REAS='add', the reference InferenceConfig's 40^3 grid
     (samples/interior/interior_multi.py:397-421), random-init weights.  The fusion neck, ProposalLayer, PyramidROIAlign and
@@ -304,11 +304,11 @@ def c4_line(dev, scenes=8, views=5, steps=3):
     import torch
     import mulit_view_object_detection_b200 as m
     from mulit_view_object_detection_b200 import synthetic as syn
-    cfg = m.FusionConfig(IMAGE_SHAPE=np.array([640, 640, 3]), NUM_VIEWS=views, IMAGES_PER_GPU=scenes, TOP_DOWN_PYRAMID_SIZE=256,
-                         NUM_CLASSES=23, nvox=40, nvox_z=40, samples=20, GRID_REAS="add", BACKBONE="resnet101",
+    cfg = m.FusionConfig(IMAGE_SHAPE=np.array([640, 640, 3]), NUM_VIEWS=views, IMAGES_PER_GPU=scenes, TOP_DOWN_PYRAMID_SIZE=channels,
+                         NUM_CLASSES=23, nvox=40, nvox_z=40, samples=20, GRID_REAS=grid_reas, BACKBONE="resnet101",
                          DETECTION_MIN_CONFIDENCE=0.0)
-    out = {"workload": "c4: MaskRCNN.predict, ResNet-101 + FPN, %d scenes x %d views, 640x640, 256-ch pyramid, 40^3 grid, GRID_REAS=add, "
-                       "1000 proposals, 100 detections + masks, random-init weights, inputs in HBM" % (scenes, views)}
+    out = {"workload": "c4: MaskRCNN.predict, ResNet-101 + FPN, %d scenes x %d views, 640x640, %d-ch pyramid, 40^3 grid, GRID_REAS=%s, "
+                       "1000 proposals, 100 detections + masks, random-init weights, inputs in HBM" % (scenes, views, channels, grid_reas)}
     with torch.no_grad():
         net = m.MaskRCNN("inference", cfg, device=dev, seed=4)
         rng = np.random.default_rng(4000)
@@ -671,6 +671,10 @@ def run_b200(args):
                     line["c4_model"] = c4_line(dev)
                 except Exception as e:                       # the headline line must not depend on the extra
                     line["c4_model"] = {"error": "%s: %s" % (type(e).__name__, e)}
+                try:                                         # the neck the reference's shipped configs use (interior_multi.py:391-419)
+                    line["c4_model_conv3d"] = c4_line(dev, grid_reas="conv3d", channels=64)
+                except Exception as e:
+                    line["c4_model_conv3d"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if c4_dp is not None:
             line["c4_model"] = c4_dp
         if world == 1 and not args.no_cpu_baseline:
