@@ -581,7 +581,6 @@ if __name__ == "__main__":
         for g in sys.argv[1:]:
             globals()[g]()
         sys.exit(0)
-    gen_model_graphs()
     gen_grid_reas()
     gen_depth_sampling()
     gen_unproject_project()
@@ -593,3 +592,4 @@ if __name__ == "__main__":
     gen_convlstm()
     gen_convlstm_sequence()
     gen_poses()
+    gen_model_graphs()          # last: it swaps in its own stand-ins for the Keras layers
