@@ -714,9 +714,9 @@ def proj_grid_depth_sampling(inputs, config, proj_size, name, params=None, view=
 def unproject_fuse_project(feats, Rcam, Kmat, config, proj_size, mode="sum", bn=None, relu_out=False,
                            grid_out=None, out=None, tensor_cores=None):
     """The fused pipeline: unproj_feat -> grid_reas(sum|mean|max [+BN+ReLU]) -> proj_grid; returns (ray slices [B,S,P,P,C],
-    fused grid [B,X,Y,Z,C]).  One C call (``mvf_unproject_fuse_project``): for the configurations K1T accepts, the feature split,
-    the tensor-core unprojection and the projection are queued with programmatic stream serialization and overlap scene by scene
-    (same kernels, same bits as ``unproject_fuse`` followed by ``proj_grid``); otherwise slot kernel, then projection.
+    fused grid [B,X,Y,Z,C]).  One C call (``mvf_unproject_fuse_project``): K1T with its feature split running under it (or the slot
+    kernel for the modes K1T does not take), then the projection reading the main-view poses in place -- same kernels, same bits
+    as ``unproject_fuse`` followed by ``proj_grid``.
     ``tensor_cores=False`` forces the two plain calls on the slot kernel."""
     if tensor_cores is False:
         fused = unproject_fuse(feats, Rcam, Kmat, config, mode=mode, bn=bn, relu_out=relu_out, out=grid_out, tensor_cores=False)
