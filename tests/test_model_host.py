@@ -108,3 +108,35 @@ def test_named_weights_round_trip(tmp_path):
             assert np.array_equal(np.asarray(a, np.float32).reshape(-1), np.asarray(b, np.float32).reshape(-1)), name
     with pytest.raises(ValueError):
         m.MaskRCNN("training", cfg, device="cpu")
+
+
+def test_mold_and_unmold_round_trip_on_host():
+    """mold_inputs / unmold_detections (model_multi.py:2915-3017) are pure host code: a detection given in normalised coordinates of
+    the padded network input comes back in pixels of the ORIGINAL image, zero-area boxes are dropped, masks land inside their boxes."""
+    import mulit_view_object_detection_b200 as m
+    cfg = graph_cfg()
+    cfg.IMAGE_MIN_DIM = cfg.IMAGE_MAX_DIM = 64
+    net = m.MaskRCNN("inference", cfg, device="cpu")
+    views = [np.full((48, 64, 3), 100 + i, np.uint8) for i in range(2)]
+    molded, metas, windows = net.mold_inputs(views)
+    assert molded.shape == (2, 64, 64, 3) and molded.dtype == np.float64      # float32 image - float64 MEAN_PIXEL, as in the reference
+    assert np.allclose(molded[0, 8, 0], 100 - np.array([123.7, 116.8, 103.9])) and np.allclose(molded[0, 0, 0], -np.array([123.7, 116.8, 103.9]))
+    assert tuple(windows[0]) == (8, 0, 56, 64) and metas.shape == (2, 12 + cfg.NUM_CLASSES)
+    assert tuple(metas[0, 1:4]) == (48, 64, 3) and tuple(metas[0, 4:7]) == (64, 64, 3) and tuple(metas[0, 7:11]) == (8, 0, 56, 64)
+    # a box covering rows 20..40, columns 16..48 of the molded image = rows 12..32 of the original
+    box_px = np.array([[20, 16, 40, 48]], np.float32)
+    det = np.zeros((4, 6), np.float32)
+    det[0, :4] = MH.norm_boxes(box_px, (64, 64))[0]
+    det[0, 4:] = (3, 0.9)
+    det[1, :4] = MH.norm_boxes(np.array([[30, 30, 30, 40]], np.float32), (64, 64))[0]      # zero height: dropped
+    det[1, 4:] = (2, 0.8)
+    masks = np.zeros((4, 28, 28, cfg.NUM_CLASSES), np.float32)
+    masks[0, :, :, 3] = 1.0
+    masks[0, :, :14, 3] = 0.2                                   # left half below the 0.5 threshold
+    masks[1, :, :, 2] = 1.0
+    boxes, class_ids, scores, full = net.unmold_detections(det, masks, (48, 64, 3), (64, 64, 3), windows[0])
+    assert boxes.tolist() == [[12, 16, 32, 48]] and class_ids.tolist() == [3] and np.allclose(scores, [0.9])
+    assert full.shape == (48, 64, 1) and full.dtype == bool
+    assert full[12:32, 32:48, 0].all() and not full[12:32, 16:32, 0].any() and full.sum() == 20 * 16
+    none = net.unmold_detections(np.zeros((4, 6), np.float32), masks, (48, 64, 3), (64, 64, 3), windows[0])
+    assert none[0].shape == (0, 4) and none[3].shape == (48, 64, 0)
